@@ -1,0 +1,142 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference,
+CPU, fp32) on seeded synthetic inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference hard-codes CUDA in two places (utils/mpi/homography_sampler.py:16-17); for a CPU run
+they are shimmed: torch.cuda.synchronize -> no-op, Tensor.cuda -> identity.  Nothing of the
+reference is copied: only its outputs are stored.  The splat fixtures come from the reference's
+warping.c compiled from source by oracle/Makefile (oracle/_ref/libwarping_ref.so).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("MPIFLOW_REFERENCE", "/root/reference")
+
+torch.cuda.synchronize = lambda *a, **k: None
+torch.Tensor.cuda = lambda self, *a, **k: self
+sys.path.insert(0, REF)
+from utils.mpi import mpi_rendering as ref_render          # noqa: E402
+from utils.mpi.homography_sampler import HomographySample  # noqa: E402
+import geometry as ref_geometry                            # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "mpi-flow_b200"))
+sys.path.insert(0, ROOT)
+import synth                                               # noqa: E402
+from oracle import mpi_oracle                              # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+T = torch.from_numpy
+
+
+def run_render(inp, keep_inputs, **flags):
+    """reference xyz_src + xyz_tgt + render_tgt_rgb_depth on a synth.frame_inputs dict"""
+    mpi, disp, G, Kinv, K = (T(inp[k]) for k in ("mpi", "disparity", "G", "Kinv", "K"))
+    B, S, _, H, W = mpi.shape
+    sampler = HomographySample(H, W, torch.device("cpu"))
+    xyz_src = ref_render.get_src_xyz_from_plane_disparity(sampler.meshgrid, disp, Kinv)
+    xyz_tgt = ref_render.get_tgt_xyz_from_plane_disparity(xyz_src, G)
+    obj = T(inp["obj_mask"]).unsqueeze(1).repeat(1, S, 1, 1, 1)
+    rgb, depth, mask, flow, obj_out = ref_render.render_tgt_rgb_depth(
+        sampler, mpi[:, :, 0:3], mpi[:, :, 3:], disp, xyz_tgt, xyz_src, G, Kinv, K,
+        None, use_alpha=False, obj_mask=obj, **flags)
+    out = dict(out_rgb=rgb, out_depth=depth, out_mask=mask, out_flow=flow, out_obj=obj_out)
+    out = {k: v.numpy() for k, v in out.items()}
+    if keep_inputs:
+        out.update({"in_" + k: v for k, v in inp.items()})
+    return out, (sampler, xyz_src, xyz_tgt)
+
+
+def save(name, **arrs):
+    p = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(p, **arrs)
+    print(f"{name}: {os.path.getsize(p) / 1024:.0f} KiB")
+
+
+def main():
+    # ---- whole-frame cases (inputs regenerable from synth + the stored meta) ------------------
+    cases = {
+        # name: (B, S, H, W, kind, pose, seed, flags)
+        "frame_white_random": (2, 6, 40, 56, "white", "random", 114514, {}),
+        "frame_smooth_regression": (1, 8, 48, 64, "smooth", "regression", 114515, {}),
+        "frame_identity": (1, 5, 32, 48, "white", "identity", 114516, {}),
+        "frame_object_pose_flags": (1, 6, 36, 52, "smooth", "object", 114517,
+                                    dict(is_bg_depth_inf=True, hard_flow=True)),
+        "frame_wide_1280": (1, 4, 16, 1280, "white", "random", 114518, {}),
+        "frame_c1_256": (1, 32, 256, 256, "smooth", "identity", 114519, {}),
+    }
+    for name, (B, S, H, W, kind, pose, seed, flags) in cases.items():
+        inp = synth.frame_inputs(B, S, H, W, kind, pose, seed)
+        small = inp["mpi"].nbytes < (1 << 20)
+        out, _ = run_render(inp, keep_inputs=small, **flags)
+        meta = np.array([B, S, H, W, seed], np.int64)
+        save(name, meta=meta, kind=kind, pose=pose, is_bg_depth_inf=bool(flags.get("is_bg_depth_inf", False)),
+             hard_flow=bool(flags.get("hard_flow", False)), **out)
+
+    # ---- per-function intermediates on one tiny case -------------------------------------------
+    inp = synth.frame_inputs(2, 5, 24, 40, "white", "random", 114520)
+    mpi, disp, G, Kinv, K = (T(inp[k]) for k in ("mpi", "disparity", "G", "Kinv", "K"))
+    B, S, _, H, W = mpi.shape
+    _, (sampler, xyz_src, xyz_tgt) = run_render(inp, False)
+    rep = lambda m: m.unsqueeze(1).repeat(1, S, 1, 1).reshape(B * S, *m.shape[1:])
+    depth = torch.reciprocal(disp).view(B * S)
+    src = torch.cat((mpi, xyz_tgt), dim=2).view(B * S, 7, H, W)
+    warped, valid, flowB2A = sampler.sample(src, depth, rep(G), rep(Kinv), rep(K))
+    flowA2B = sampler.sample_inverse(src, depth, rep(G), rep(Kinv), rep(K))
+    w5 = warped.view(B, S, 7, H, W)
+    pvr = ref_render.plane_volume_rendering(
+        w5[:, :, 0:3], w5[:, :, 3:4], w5[:, :, 4:7], mpi[:, :, 3:],
+        flowA2B.permute(0, 3, 1, 2).reshape(B, S, 2, H, W), xyz_src, False,
+        obj_mask=T(inp["obj_mask"]).unsqueeze(1).repeat(1, S, 1, 1, 1))
+    pvr_bg = ref_render.plane_volume_rendering(w5[:, :, 0:3], w5[:, :, 3:4], w5[:, :, 4:7], None, None, None, True)
+    flow_soft = ref_render.plane_volume_rendering_flow(
+        mpi[:, :, 3:], flowA2B.permute(0, 3, 1, 2).reshape(B, S, 2, H, W), xyz_src, False, hard_flow=False)
+    flow_hard = ref_render.plane_volume_rendering_flow(
+        mpi[:, :, 3:], flowA2B.permute(0, 3, 1, 2).reshape(B, S, 2, H, W), xyz_src, False, hard_flow=True)
+    alpha = torch.clamp(mpi[:, :, 3:], 0, 1)
+    ac_rgb, ac_w = ref_render.alpha_composition(alpha, mpi[:, :, 0:3])
+    # NOTE: ref_render.render(..., use_alpha=True) raises UnboundLocalError in the reference
+    # (utils/mpi/mpi_rendering.py:33-39 never binds flowA2B), so that branch has no golden.
+    save("functions_tiny", meta=np.array([B, S, H, W, 114520], np.int64),
+         **{"in_" + k: v for k, v in inp.items()},
+         meshgrid=sampler.meshgrid.numpy(), xyz_src=xyz_src.numpy(), xyz_tgt=xyz_tgt.numpy(),
+         warped=warped.numpy(), valid=valid.numpy(), flowB2A=flowB2A.numpy(), flowA2B=flowA2B.numpy(),
+         pvr_rgb=pvr[0].numpy(), pvr_depth=pvr[1].numpy(), pvr_tacc=pvr[2].numpy(), pvr_weights=pvr[3].numpy(),
+         pvr_flow=pvr[4].numpy(), pvr_obj=pvr[5].numpy(), pvr_bg_depth=pvr_bg[1].numpy(),
+         flow_soft=flow_soft.numpy(), flow_hard=flow_hard.numpy(),
+         ac_rgb=ac_rgb.numpy(), ac_w=ac_w.numpy())
+
+    # ---- geometry.py ------------------------------------------------------------------------------
+    rng = np.random.default_rng(7)
+    aa = (rng.standard_normal((4, 1, 3)) * 0.05).astype(np.float32)
+    aa[3] = 0.0                                                   # zero rotation (moving_obj.py:94)
+    tr = (rng.standard_normal((4, 1, 3)) * 0.2).astype(np.float32)
+    M = ref_geometry.transformation_from_parameters(T(aa), T(tr)).numpy()
+    Mi = ref_geometry.transformation_from_parameters(T(aa), T(tr), invert=True).numpy()
+    h, w = 20, 28
+    K4 = np.eye(4, dtype=np.float32)[None]; K4[0, :3, :3] = synth.intrinsics(h, w)[0]
+    K4i = np.eye(4, dtype=np.float32)[None]; K4i[0, :3, :3] = synth.intrinsics_inv(synth.intrinsics(h, w))[0]
+    dep = (rng.random((1, 1, h, w)) * 5 + 0.5).astype(np.float32)
+    cam = ref_geometry.BackprojectDepth(1, h, w)(T(dep), T(K4i))
+    pix, z = ref_geometry.Project3D(1, h, w)(cam, T(K4), T(M[:1]))
+    save("geometry", axisangle=aa, translation=tr, M=M, M_invert=Mi, K4=K4, K4inv=K4i, depth=dep,
+         cam_points=cam.numpy(), pix_coords=pix.numpy(), z=z.numpy())
+
+    # ---- forward splat (reference warping.c compiled from source) ----------------------------------
+    splat = {}
+    for tag, (h, w, mode, seed) in {"dense": (48, 64, "dense", 1), "pile": (40, 40, "pile", 2),
+                                    "identity": (16, 24, "identity", 3), "row": (1, 97, "dense", 4),
+                                    "kitti_strip": (24, 1280, "dense", 5)}.items():
+        src, idx, idy, z = synth.splat_inputs(h, w, seed, mode)
+        out = mpi_oracle.forward_warping(src, idx, idy, z, use_ref=True)
+        splat.update({f"{tag}_meta": np.array([h, w, seed], np.int64), f"{tag}_mode": mode, f"{tag}_warped": out})
+    save("splat", **splat)
+
+
+if __name__ == "__main__":
+    main()
