@@ -1,0 +1,133 @@
+/*
+ * mpiflow.h -- C ABI of libmpiflow_sm100.so: the B200 (sm_100a) implementation of MPI-Flow's
+ * multiplane-image renderer hot path and depth-aware forward splat.
+ *
+ * Conventions
+ *   - every entry point is extern "C", takes plain pointers / sizes, returns int:
+ *       0 = success, >0 = a cudaError_t, <0 = MPIFLOW_E_* argument error.  Nothing throws.
+ *   - "_f32" entry points take DEVICE pointers and a cudaStream_t (passed as void*); they never
+ *     allocate, never synchronise and keep no global state: scratch comes from the caller
+ *     (size from the matching *_workspace_bytes()).
+ *   - "_host" entry points (and the legacy forward_warping) take HOST pointers, do their own
+ *     H2D/D2H and return when the result is in the caller's buffers.
+ *   - tensors are fp32, the two innermost dims (H, W) contiguous; outer strides are given in
+ *     ELEMENTS so that torch views (mpi[:, :, 0:3], expand()ed masks) are accepted as they are.
+ *   - reference citations are relative to the MPI-Flow repository root.
+ */
+#ifndef MPIFLOW_H_
+#define MPIFLOW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPIFLOW_VERSION 100
+
+#define MPIFLOW_E_BADARG (-1)    /* null pointer / non-positive size / unsupported value */
+#define MPIFLOW_E_WORKSPACE (-2) /* workspace too small */
+#define MPIFLOW_E_SINGULAR (-3)  /* "Matrix inverse contains nan!" (homography_sampler.py:24-26) */
+#define MPIFLOW_E_NODEVICE (-4)  /* no sm_100 device / CUDA not initialised */
+
+/* render flags (keyword arguments of mpi_rendering.render_tgt_rgb_depth, mpi_rendering.py:259-272) */
+#define MPIFLOW_BG_DEPTH_INF 1u /* is_bg_depth_inf */
+#define MPIFLOW_HARD_FLOW 2u    /* hard_flow */
+
+int mpiflow_version(void);
+/* static string for any code returned by this library */
+const char *mpiflow_error_string(int code);
+
+/* ---- a4/a5 prologue: plane-induced homographies ------------------------------------------------
+ * Replaces the host-side maths of HomographySample.sample / sample_inverse
+ * (utils/mpi/homography_sampler.py:96-122, :176-197): H_tgt_src = K_tgt (R - t n^T / -d) K_src^-1 in
+ * fp32 (cuBLAS accumulation order), H_src_tgt = fp32(inverse_fp64(H_tgt_src)).  The reference does the
+ * inverse on the CPU with a device sync; here it is a device kernel, no sync.
+ *   G [N,4,4], Kinv [N,3,3], Kt [N,3,3], depth [N]  ->  Hts [N,9], Hst [N,9]
+ *   status: device int, set non-zero if any inverse is singular / NaN (may be NULL). */
+int mpiflow_plane_homographies_f32(const float *G, const float *Kinv, const float *Kt, const float *depth,
+                                   int N, float *Hts, float *Hst, int *status, void *stream);
+
+/* ---- a10: fused render_tgt_rgb_depth -----------------------------------------------------------
+ * One launch replaces get_src_xyz_from_plane_disparity + get_tgt_xyz_from_plane_disparity +
+ * HomographySample.sample + sample_inverse + render (plane_volume_rendering +
+ * plane_volume_rendering_flow) + the tgt_mask reduction: mpi_rendering.py:213-256, :259-349,
+ * homography_sampler.py:80-220, for the sigma mode (use_alpha=False) with plane-derived xyz.
+ *
+ *   rgb    [B,S,3,H,W]  strides (rgb_sb, rgb_ss, rgb_sc)      sigma [B,S,1,H,W] strides (sig_sb, sig_ss)
+ *   obj    [B,S,1,H,W]  strides (obj_sb, obj_ss); obj_ss = 0 for a mask shared by all planes
+ *   disparity [B,S] (dense), G [B,4,4], Kinv [B,3,3], Kt [B,3,3]
+ *   out_rgb [B,3,H,W], out_depth [B,1,H,W], out_mask [B,1,H,W] (count of valid planes, :347),
+ *   out_flow [B,2,H,W] (flowA2B, source frame), out_obj [B,1,H,W]      -- all dense
+ *   workspace: mpiflow_render_workspace_bytes(B, S) bytes, device, 16-byte aligned
+ *   status: device int (may be NULL), non-zero when a homography was singular */
+size_t mpiflow_render_workspace_bytes(int B, int S);
+int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
+                             const float *sigma, int64_t sig_sb, int64_t sig_ss,
+                             const float *obj, int64_t obj_sb, int64_t obj_ss,
+                             const float *disparity, const float *G, const float *Kinv, const float *Kt,
+                             int B, int S, int H, int W, unsigned flags,
+                             float *out_rgb, float *out_depth, float *out_mask, float *out_flow,
+                             float *out_obj, void *workspace, size_t workspace_bytes, int *status,
+                             void *stream);
+
+/* Same computation from HOST buffers (dense layouts: mpi [B,S,4,H,W] = rgb+sigma, obj [B,1,H,W]):
+ * H2D of the inputs, the two launches, D2H of the five outputs, all inside the call; returns
+ * MPIFLOW_E_SINGULAR like the reference raises.  Frames are pipelined over two streams. */
+int mpiflow_render_fused_host(const float *mpi, const float *obj, const float *disparity, const float *G,
+                              const float *Kinv, const float *Kt, int B, int S, int H, int W,
+                              unsigned flags, float *out_rgb, float *out_depth, float *out_mask,
+                              float *out_flow, float *out_obj);
+
+/* ---- fine-grained operators (same maths, un-fused, arbitrary tensors) ---------------------------- */
+/* a4  HomographySample.sample (homography_sampler.py:124-158): src [N,C,H,W] (dense) warped by Hst
+ *     [N,9] -> tgt [N,C,H,W], valid [N,H,W] (u8 0/1), flowB2A [N,H,W,2] (either may be NULL) */
+int mpiflow_homography_sample_f32(const float *src, const float *Hst, int N, int C, int H, int W,
+                                  float *tgt, uint8_t *valid, float *flowB2A, void *stream);
+/* a5  HomographySample.sample_inverse (:199-220): Hts [N,9] -> flowA2B [N,H,W,2] */
+int mpiflow_homography_flow_f32(const float *Hts, int N, int H, int W, float *flowA2B, void *stream);
+/* a2  get_src_xyz_from_plane_disparity (mpi_rendering.py:213-239) -> xyz [B,S,3,H,W] */
+int mpiflow_src_xyz_f32(const float *Kinv, const float *disparity, int B, int S, int H, int W,
+                        float *xyz, void *stream);
+/* a3  get_tgt_xyz_from_plane_disparity (:242-256) / transform_G_xyz (rendering_utils.py:4-23) */
+int mpiflow_tgt_xyz_f32(const float *xyz_src, const float *G, int B, int S, int H, int W,
+                        float *xyz_tgt, void *stream);
+/* a7  plane_volume_rendering + weighted_sum_mpi (:62-99, :142-154).  rgb [B,S,3,H,W], sigma
+ *     [B,S,1,H,W], xyz [B,S,3,H,W] dense; src_flow [B,S,2,H,W] / obj [B,S,1,H,W] both or neither.
+ *     Any output may be NULL: rgb_out [B,3,H,W], depth_out [B,1,H,W], transparency_acc [B,S,1,H,W],
+ *     weights [B,S,1,H,W], flow_out [B,2,H,W], obj_out [B,1,H,W]. */
+int mpiflow_plane_volume_rendering_f32(const float *rgb, const float *sigma, const float *xyz,
+                                       const float *src_flow, const float *obj, int B, int S, int H, int W,
+                                       unsigned flags, float *rgb_out, float *depth_out,
+                                       float *transparency_acc, float *weights, float *flow_out,
+                                       float *obj_out, void *stream);
+/* a8  plane_volume_rendering_flow (:102-139) -> flow_out [B,2,H,W] */
+int mpiflow_plane_volume_rendering_flow_f32(const float *src_sigma, const float *src_flow,
+                                            const float *src_xyz, int B, int S, int H, int W,
+                                            unsigned flags, float *flow_out, void *stream);
+/* a9  alpha_composition (:42-59): alpha [B,K,1,H,W], value [B,K,C,H,W] -> composed [B,C,H,W],
+ *     weights [B,K,1,H,W] (may be NULL) */
+int mpiflow_alpha_composition_f32(const float *alpha, const float *value, int B, int K, int C, int H,
+                                  int W, float *composed, float *weights, void *stream);
+
+/* ---- a6: depth-aware forward splat ---------------------------------------------------------------
+ * Legacy symbol, identical signature and semantics to external/forward_warping/warping.c:6
+ * (HOST pointers; src u8[h,w,3], idx/idy int64[h,w], z f32[h,w], warped u8[h,w,5] pre-zeroed by the
+ * caller; no return value).  Bit-exact with the serial C loop, computed on the GPU.
+ * Also exported by external/forward_warping/libwarping.so for moving_obj.py:12-13. */
+void forward_warping(const void *src, const void *idx, const void *idy, const void *z, void *warped,
+                     int h, int w);
+/* like forward_warping but reports errors */
+int mpiflow_forward_warp_host(const void *src, const void *idx, const void *idy, const void *z,
+                              void *warped, int h, int w);
+/* DEVICE pointers, same buffers; warped must hold the caller's initial content (normally zeros). */
+size_t mpiflow_forward_warp_workspace_bytes(int h, int w);
+int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx, const int64_t *idy, const float *z,
+                             uint8_t *warped, int h, int w, void *workspace, size_t workspace_bytes,
+                             void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPIFLOW_H_ */

@@ -1,0 +1,44 @@
+"""Build libmpiflow_sm100.so (and the drop-in external/forward_warping/libwarping.so) in-tree.
+
+    python mpi-flow_b200/build.py [--force]
+
+Plain nvcc, sm_100a only, no torch/pybind headers: the product is a C-ABI shared library.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmpiflow_sm100.so")
+WARPLIB = os.path.join(HERE, "external", "forward_warping", "libwarping.so")
+SOURCES = ["api.cu", "homography.cu", "render_fused.cu", "composite.cu", "splat.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "nvcc")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mpiflow.h")]
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    extra = ["-Xptxas", "-v"] if verbose else []
+    if force or _stale(LIB, deps):
+        subprocess.check_call([nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + srcs)
+    if force or _stale(WARPLIB, deps):
+        os.makedirs(os.path.dirname(WARPLIB), exist_ok=True)
+        # same symbol, same relative path as the reference loads (moving_obj.py:12-13): the same binary
+        shutil.copyfile(LIB, WARPLIB)
+        os.chmod(WARPLIB, 0o755)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

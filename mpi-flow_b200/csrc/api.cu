@@ -1,0 +1,102 @@
+// api.cu -- library-level entry points: version, error strings and the host-buffer renderer.
+#include <mutex>
+
+#include "common.cuh"
+
+MPIFLOW_API int mpiflow_version(void) { return MPIFLOW_VERSION; }
+
+MPIFLOW_API const char *mpiflow_error_string(int code)
+{
+    switch (code) {
+        case 0: return "success";
+        case MPIFLOW_E_BADARG: return "mpiflow: bad argument (null pointer, non-positive size or unsupported value)";
+        case MPIFLOW_E_WORKSPACE: return "mpiflow: workspace too small";
+        case MPIFLOW_E_SINGULAR: return "Matrix inverse contains nan!";
+        case MPIFLOW_E_NODEVICE: return "mpiflow: no CUDA device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "mpiflow: unknown error";
+    }
+}
+
+namespace {
+struct HostCtx {
+    std::mutex mu;
+    void *buf = nullptr;
+    size_t cap = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+};
+HostCtx g_ctx;
+inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+}  // namespace
+
+// Host-buffer variant of mpiflow_render_fused_f32: frames are double-buffered over two streams so
+// the H2D of frame b+1 overlaps the kernels and D2H of frame b (pinned host memory gets full PCIe
+// bandwidth; pageable memory works but is staged by the driver).
+MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, const float *disparity,
+                                          const float *G, const float *Kinv, const float *Kt, int B, int S,
+                                          int H, int W, unsigned flags, float *out_rgb, float *out_depth,
+                                          float *out_mask, float *out_flow, float *out_obj)
+{
+    MF_CHECK_ARG(mpi && disparity && G && Kinv && Kt && out_rgb && out_depth && out_mask && out_flow);
+    MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0);
+    std::lock_guard<std::mutex> lock(g_ctx.mu);
+    cudaError_t e;
+    for (int i = 0; i < 2; i++)
+        if (!g_ctx.streams[i] && (e = cudaStreamCreateWithFlags(&g_ctx.streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+            return e == cudaErrorNoDevice ? MPIFLOW_E_NODEVICE : (int)e;
+
+    const size_t HW = (size_t)H * W;
+    const size_t b_mpi = al256(HW * 4 * S * sizeof(float)), b_obj = al256(HW * sizeof(float));
+    const size_t b_small = al256((S + 16 + 9 + 9) * sizeof(float)), b_out = al256(HW * 8 * sizeof(float));
+    const size_t b_ws = al256(mpiflow_render_workspace_bytes(1, S));
+    const size_t slot = b_mpi + b_obj + b_small + b_out + b_ws;
+    const size_t need = 2 * slot + al256((size_t)B * sizeof(int));
+    if (need > g_ctx.cap) {
+        if (g_ctx.buf) cudaFree(g_ctx.buf);
+        g_ctx.buf = nullptr; g_ctx.cap = 0;
+        if ((e = cudaMalloc(&g_ctx.buf, need)) != cudaSuccess) return (int)e;
+        g_ctx.cap = need;
+    }
+    char *base = reinterpret_cast<char *>(g_ctx.buf);
+    int *d_status = reinterpret_cast<int *>(base + 2 * slot);
+
+    for (int b = 0; b < B; b++) {
+        cudaStream_t st = g_ctx.streams[b & 1];
+        char *d = base + (size_t)(b & 1) * slot;
+        float *d_mpi = (float *)d, *d_obj = (float *)(d + b_mpi);
+        float *d_small = (float *)(d + b_mpi + b_obj);
+        float *d_disp = d_small, *d_G = d_small + S, *d_Kinv = d_G + 16, *d_Kt = d_Kinv + 9;
+        float *d_out = (float *)(d + b_mpi + b_obj + b_small);
+        void *d_ws = d + b_mpi + b_obj + b_small + b_out;
+        if ((e = cudaMemcpyAsync(d_mpi, mpi + (size_t)b * S * 4 * HW, HW * 4 * S * sizeof(float),
+                                 cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+        if (obj) cudaMemcpyAsync(d_obj, obj + (size_t)b * HW, HW * sizeof(float), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_disp, disparity + (size_t)b * S, S * sizeof(float), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_G, G + (size_t)b * 16, 16 * sizeof(float), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_Kinv, Kinv + (size_t)b * 9, 9 * sizeof(float), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_Kt, Kt + (size_t)b * 9, 9 * sizeof(float), cudaMemcpyHostToDevice, st);
+        float *o_rgb = d_out, *o_depth = d_out + 3 * HW, *o_mask = d_out + 4 * HW, *o_flow = d_out + 5 * HW,
+              *o_obj = d_out + 7 * HW;
+        const int rc = mpiflow_render_fused_f32(
+            d_mpi, (int64_t)S * 4 * HW, (int64_t)4 * HW, (int64_t)HW, d_mpi + 3 * HW, (int64_t)S * 4 * HW,
+            (int64_t)4 * HW, obj ? d_obj : nullptr, (int64_t)HW, 0, d_disp, d_G, d_Kinv, d_Kt, 1, S, H, W,
+            flags, o_rgb, o_depth, o_mask, o_flow, (obj && out_obj) ? o_obj : nullptr, d_ws, b_ws,
+            d_status + b, st);
+        if (rc) return rc;
+        cudaMemcpyAsync(out_rgb + (size_t)b * 3 * HW, o_rgb, 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_depth + (size_t)b * HW, o_depth, HW * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_mask + (size_t)b * HW, o_mask, HW * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_flow + (size_t)b * 2 * HW, o_flow, 2 * HW * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (obj && out_obj)
+            cudaMemcpyAsync(out_obj + (size_t)b * HW, o_obj, HW * sizeof(float), cudaMemcpyDeviceToHost, st);
+    }
+    for (int i = 0; i < 2; i++)
+        if ((e = cudaStreamSynchronize(g_ctx.streams[i])) != cudaSuccess) return (int)e;
+    // error behaviour of homography_sampler.inverse (:24-26): raise when an inverse is NaN
+    int bad = 0;
+    for (int b = 0; b < B && !bad; b++) {
+        int v = 0;
+        if ((e = cudaMemcpy(&v, d_status + b, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return (int)e;
+        bad |= v;
+    }
+    return bad ? MPIFLOW_E_SINGULAR : 0;
+}

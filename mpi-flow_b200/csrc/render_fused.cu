@@ -1,0 +1,241 @@
+// render_fused.cu -- the fused MPI renderer (SURVEY.md section 8, rows a2+a3+a4+a5+a7+a8+a10).
+//
+// One thread per pixel index p = (x, y).  The same index is used twice, as in the reference:
+//   * as TARGET pixel q: for every plane s the plane homography H_src_tgt maps q to a source
+//     position, the RGBA (+ object mask) plane is sampled there bilinearly with border clamp
+//     (homography_sampler.py:124-158 -> F.grid_sample), the plane's target-frame xyz is evaluated at
+//     the clamped position, and the stack is over-composited front to back
+//     (mpi_rendering.py:62-99, :142-154, :329-347);
+//   * as SOURCE pixel p: H_tgt_src gives the per-plane forward flow (homography_sampler.py:199-220),
+//     volume-rendered with the weights of the UN-warped sigma (mpi_rendering.py:102-139).
+// Running transmittances, colour, depth, flow, mask and count accumulators live in registers for
+// the whole plane loop; nothing of size [B,S,*,H,W] is ever written.
+//
+// Algorithmic HBM bytes per frame: 4*H*W*(4S + 1 + 8)   (RGBA once, mask once, 8 output channels).
+#include "homography.cuh"
+
+struct RenderParams {
+    const float *rgb;   int64_t rgb_sb, rgb_ss, rgb_sc;
+    const float *sigma; int64_t sig_sb, sig_ss;
+    const float *obj;   int64_t obj_sb, obj_ss;
+    const PlaneConst *pc;  // [B*S]
+    const float *Kinv;     // [B,3,3]
+    int B, S, H, W;
+    unsigned flags;
+    float *out_rgb, *out_depth, *out_mask, *out_flow, *out_obj;
+};
+
+// prologue: PlaneConst for every (b, s); inputs are per batch.
+__global__ void plane_consts_kernel(const float *__restrict__ G, const float *__restrict__ Kinv,
+                                    const float *__restrict__ Kt, const float *__restrict__ disparity,
+                                    int B, int S, PlaneConst *__restrict__ pc, int *__restrict__ status)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= B * S) return;
+    const int b = n / S, s = n % S;
+    float g[16], ki[9], kt[9];
+    for (int i = 0; i < 16; i++) g[i] = G[(size_t)b * 16 + i];
+    for (int i = 0; i < 9; i++) { ki[i] = Kinv[(size_t)b * 9 + i]; kt[i] = Kt[(size_t)b * 9 + i]; }
+    const float depth = __frcp_rn(disparity[n]);  // torch.reciprocal (mpi_rendering.py:278)
+    PlaneConst c;
+    const bool ok = plane_homography(g, ki, kt, depth, c.hts, c.hst);
+    // xyz_tgt(ix,iy) = G . [ (Kinv (ix,iy,1)) * depth ; 1 ]  ==  (depth * R Kinv) (ix,iy,1) + t
+    // (mpi_rendering.py:213-256, rendering_utils.py:4-23; affine in the pixel position, so the
+    //  reference's bilinear sample of the xyz tensor equals this evaluated at the clamped index)
+    float R[9], M[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) R[i * 3 + j] = g[i * 4 + j];
+    mm33_fma(R, ki, M);
+    for (int i = 0; i < 9; i++) c.P[i] = __fmul_rn(M[i], depth);
+    for (int i = 0; i < 3; i++) c.P[i * 3 + 2] = __fadd_rn(c.P[i * 3 + 2], g[i * 4 + 3]);
+    c.depth = depth;
+    c.ddepth = (s + 1 < S) ? __fsub_rn(__frcp_rn(disparity[n + 1]), depth) : 0.f;
+    c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
+    pc[n] = c;
+    if (!ok && status) atomicExch(status, 1);
+}
+
+// front-to-back accumulator of one frame (mpi_rendering.py:79-96, :143-152)
+struct TgtAcc {
+    float acc = 1.f, r = 0.f, g = 0.f, b = 0.f, zsum = 0.f, wsum = 0.f, obj = 0.f;
+    __device__ __forceinline__ void add(float sigma, float dist, float cr, float cg, float cb, float z,
+                                        float m)
+    {
+        const float T = __expf(-sigma * dist);  // :79
+        const float w = acc * (1.f - T);        // :80, :89
+        acc *= (T + 1e-6f);                     // :84
+        wsum += w;
+        r = fmaf(w, cr, r);
+        g = fmaf(w, cg, g);
+        b = fmaf(w, cb, b);
+        zsum = fmaf(w, z, zsum);
+        obj = fmaf(w, m, obj);
+    }
+};
+
+template <bool HAS_OBJ>
+__global__ void __launch_bounds__(256)
+render_fused_kernel(const RenderParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PlaneConst *spc = reinterpret_cast<PlaneConst *>(smem_raw);
+    const int b = blockIdx.z;
+    const int S = p.S, H = p.H, W = p.W;
+    {   // stage this batch entry's plane constants: S * 128 B
+        const float4 *src = reinterpret_cast<const float4 *>(p.pc + (size_t)b * S);
+        float4 *dst = reinterpret_cast<float4 *>(spc);
+        for (int i = threadIdx.x; i < S * 8; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+
+    const float xf = (float)x, yf = (float)y, Wf = (float)W, Hf = (float)H;
+    const float rW = __frcp_rn(Wf * 0.5f), rH = __frcp_rn(Hf * 0.5f);
+    const size_t HW = (size_t)H * W, q = (size_t)y * W + x;
+
+    // source-frame ray length |Kinv (x,y,1)|: xyz_src = ray * depth (mpi_rendering.py:234-236), so
+    // the spacing of consecutive planes along it is |ray| * (depth[s+1] - depth[s])   (:104-107)
+    float vnorm;
+    {
+        const float *k = p.Kinv + (size_t)b * 9;
+        const float v0 = mf_dot3(__ldg(k + 0), __ldg(k + 1), __ldg(k + 2), xf, yf);
+        const float v1 = mf_dot3(__ldg(k + 3), __ldg(k + 4), __ldg(k + 5), xf, yf);
+        const float v2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
+        vnorm = sqrtf(fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
+    }
+
+    const float *rgb_b = p.rgb + (size_t)b * p.rgb_sb;
+    const float *sig_b = p.sigma + (size_t)b * p.sig_sb;
+    const float *obj_b = HAS_OBJ ? p.obj + (size_t)b * p.obj_sb : nullptr;
+
+    TgtAcc t;
+    float cnt = 0.f;
+    // plane s-1 waits for plane s's xyz to know its thickness (:68-71)
+    float pr = 0.f, pg = 0.f, pb = 0.f, psig = 0.f, pm = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+    // source frame
+    float acc_s = 1.f, fu = 0.f, fv = 0.f, best_w = -1.f;
+    const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
+
+    for (int s = 0; s < S; s++) {
+        const PlaneConst &c = spc[s];
+        // ---------------- target frame ----------------
+        const SrcPos sp = tgt_to_src(c.hst, xf, yf, Wf, Hf, rW, rH);
+        cnt += sp.valid ? 1.f : 0.f;  // :329-332, :347
+        const float x0f = floorf(sp.ix), y0f = floorf(sp.iy);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);  // weight is 0 where clamped
+        const float wx1 = __fsub_rn(__fadd_rn(x0f, 1.f), sp.ix), wx0 = __fsub_rn(sp.ix, x0f);
+        const float wy1 = __fsub_rn(__fadd_rn(y0f, 1.f), sp.iy), wy0 = __fsub_rn(sp.iy, y0f);
+        const float nw = __fmul_rn(wx1, wy1), ne = __fmul_rn(wx0, wy1);
+        const float sw = __fmul_rn(wx1, wy0), se = __fmul_rn(wx0, wy0);
+        const int o00 = y0 * W + x0, o01 = y0 * W + x1, o10 = y1 * W + x0, o11 = y1 * W + x1;
+        auto tap = [&](const float *img) {
+            float a = __fmul_rn(__ldg(img + o00), nw);
+            a = __fmaf_rn(__ldg(img + o01), ne, a);
+            a = __fmaf_rn(__ldg(img + o10), sw, a);
+            return __fmaf_rn(__ldg(img + o11), se, a);
+        };
+        const float *rgb_s = rgb_b + (size_t)s * p.rgb_ss;
+        const float *sig_s = sig_b + (size_t)s * p.sig_ss;
+        const float cr = tap(rgb_s), cg = tap(rgb_s + p.rgb_sc), cb = tap(rgb_s + 2 * p.rgb_sc);
+        float sg = tap(sig_s);
+        const float m = HAS_OBJ ? tap(obj_b + (size_t)s * p.obj_ss) : 0.f;
+        // plane xyz in the target frame at the clamped sample position
+        const float X = fmaf(c.P[0], sp.ix, fmaf(c.P[1], sp.iy, c.P[2]));
+        const float Y = fmaf(c.P[3], sp.ix, fmaf(c.P[4], sp.iy, c.P[5]));
+        const float Z = fmaf(c.P[6], sp.ix, fmaf(c.P[7], sp.iy, c.P[8]));
+        sg = (Z >= 0.f) ? sg : 0.f;  // :334-338
+        if (s > 0) {
+            const float dx = X - px, dy = Y - py, dz = Z - pz;
+            t.add(psig, sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx))), pr, pg, pb, pz, pm);
+        }
+        pr = cr; pg = cg; pb = cb; psig = sg; pm = m; px = X; py = Y; pz = Z;
+
+        // ---------------- source frame ----------------
+        const float U = mf_dot3(c.hts[0], c.hts[1], c.hts[2], xf, yf);
+        const float V = mf_dot3(c.hts[3], c.hts[4], c.hts[5], xf, yf);
+        const float Q = mf_dot3(c.hts[6], c.hts[7], c.hts[8], xf, yf);
+        float tu, tv;
+        mf_div2(U, V, Q, tu, tv);
+        const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf);  // :212-218
+        const float dist_s = (s + 1 < S) ? vnorm * c.ddepth : 1e3f;
+        const float Ts = __expf(-__ldg(sig_s + q) * dist_s);
+        const float ws = acc_s * (1.f - Ts);
+        acc_s *= (Ts + 1e-6f);
+        if (hard) {  // one-hot of the first arg-max weight (:126-130)
+            if (ws > best_w) { best_w = ws; fu = du; fv = dv; }
+        } else {
+            fu = fmaf(ws, du, fu);
+            fv = fmaf(ws, dv, fv);
+        }
+    }
+    t.add(psig, 1e3f, pr, pg, pb, pz, pm);  // last plane: thickness 1e3 (:73-78)
+
+    float *o = p.out_rgb + (size_t)b * 3 * HW + q;
+    o[0] = t.r; o[HW] = t.g; o[2 * HW] = t.b;
+    p.out_depth[(size_t)b * HW + q] = (p.flags & MPIFLOW_BG_DEPTH_INF)
+                                          ? fmaf(1.f - t.wsum, 1000.f, t.zsum)      // :148-149
+                                          : __fdiv_rn(t.zsum, t.wsum + 1e-5f);      // :151-152
+    p.out_mask[(size_t)b * HW + q] = cnt;
+    p.out_flow[(size_t)b * 2 * HW + q] = fu;
+    p.out_flow[(size_t)b * 2 * HW + HW + q] = fv;
+    if (p.out_obj) p.out_obj[(size_t)b * HW + q] = t.obj;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+MPIFLOW_API size_t mpiflow_render_workspace_bytes(int B, int S)
+{
+    if (B <= 0 || S <= 0) return 0;
+    return align_up((size_t)B * S * sizeof(PlaneConst), 256) + 256;
+}
+
+MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
+                                         const float *sigma, int64_t sig_sb, int64_t sig_ss,
+                                         const float *obj, int64_t obj_sb, int64_t obj_ss,
+                                         const float *disparity, const float *G, const float *Kinv,
+                                         const float *Kt, int B, int S, int H, int W, unsigned flags,
+                                         float *out_rgb, float *out_depth, float *out_mask,
+                                         float *out_flow, float *out_obj, void *workspace,
+                                         size_t workspace_bytes, int *status, void *stream)
+{
+    MF_CHECK_ARG(rgb && sigma && disparity && G && Kinv && Kt && workspace);
+    MF_CHECK_ARG(out_rgb && out_depth && out_mask && out_flow);
+    MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0 && B <= 65535 && (int64_t)H * W < (1ll << 31));
+    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW)) == 0);
+    MF_CHECK_ARG(((uintptr_t)workspace & 15) == 0);
+    if (workspace_bytes < mpiflow_render_workspace_bytes(B, S)) return MPIFLOW_E_WORKSPACE;
+    const size_t smem = (size_t)S * sizeof(PlaneConst);
+    MF_CHECK_ARG(smem <= 200 * 1024);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status) {
+        cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    PlaneConst *pc = reinterpret_cast<PlaneConst *>(workspace);
+    plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, status);
+    int rc = mf_launch_status();
+    if (rc) return rc;
+
+    RenderParams p;
+    p.rgb = rgb; p.rgb_sb = rgb_sb; p.rgb_ss = rgb_ss; p.rgb_sc = rgb_sc;
+    p.sigma = sigma; p.sig_sb = sig_sb; p.sig_ss = sig_ss;
+    p.obj = obj; p.obj_sb = obj_sb; p.obj_ss = obj_ss;
+    p.pc = pc; p.Kinv = Kinv;
+    p.B = B; p.S = S; p.H = H; p.W = W; p.flags = flags;
+    p.out_rgb = out_rgb; p.out_depth = out_depth; p.out_mask = out_mask; p.out_flow = out_flow;
+    p.out_obj = out_obj;
+    dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+    auto kern = obj ? render_fused_kernel<true> : render_fused_kernel<false>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<grid, 256, smem, st>>>(p);
+    return mf_launch_status();
+}

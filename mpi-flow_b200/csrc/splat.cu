@@ -1,0 +1,293 @@
+// splat.cu -- depth-aware forward splat, bit-exact with external/forward_warping/warping.c:6-33.
+//
+// The reference is a serial raster-order loop with a "last writer" z-LUT, so its result depends on
+// the ORDER in which source pixels hit a target.  Closed form: for target T
+// with writers k1 < ... < kn in raster order and z0 := 1000,
+//     rgb(T)       = src[k_m],  m = max{ i : z_i < z_{i-1} }          (untouched if no such i)
+//     valid(T)     = 1 iff n >= 1
+//     collision(T) = 1 iff z_{n-1} == 1000   (n == 1, or the previous writer's z was exactly 1000)
+// Parallel restatement: stable LSD radix sort of the source pixels by target index (stability keeps
+// raster order inside a segment) -> every writer sees its predecessor in the sorted array -> winners
+// are marked independently, the last winner per target is an atomicMax over sorted positions.
+// Everything is integer except the single fp32 '<', so the result is deterministic.
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ROUNDS = 8;                                   // items per thread
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;            // items per block
+
+// key = target raster index (y*w + x), narrowed through int exactly like warping.c:16-17;
+// out-of-range targets (undefined behaviour in the reference) get the sentinel n and are dropped.
+__global__ void splat_keys_kernel(const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h,
+                                  int w, uint32_t n, uint32_t *__restrict__ keys,
+                                  uint32_t *__restrict__ vals, uint32_t *__restrict__ winpos)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int x = (int)idx[k], y = (int)idy[k];
+    const bool ok = (x >= 0) && (x < w) && (y >= 0) && (y < h);
+    keys[k] = ok ? (uint32_t)y * (uint32_t)w + (uint32_t)x : n;
+    vals[k] = k;
+    winpos[k] = 0;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t nblocks,
+                  uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t sh[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) sh[i] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * SORT_TILE;
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const uint32_t i = base + r * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = sh[d];
+}
+
+// exclusive scan of hist (digit-major, block-minor) by a single block
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *__restrict__ hist, uint32_t total)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < total; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = (i < total) ? hist[i] : 0;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t ws = warp_sums[lane], winc = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_sums[lane] = winc - ws;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        if (i < total) hist[i] = carry + warp_sums[wid] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[wid] + inc;
+        __syncthreads();
+    }
+}
+
+// stable scatter: item order inside a tile is (warp, round, lane); ranks come from match_any
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t n,
+                     int shift, uint32_t nblocks, const uint32_t *__restrict__ offsets,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
+{
+    __shared__ uint32_t cnt[SORT_WARPS][RADIX];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t wbase = blockIdx.x * SORT_TILE + wid * (SORT_ROUNDS * 32);
+    uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool live = i < n;
+        key[r] = live ? keys_in[i] : 0xffffffffu;
+        val[r] = live ? vals_in[i] : 0;
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const uint32_t d = (key[r] >> shift) & (RADIX - 1);
+            const unsigned peers = __match_any_sync(act, d);
+            if (lane == __ffs(peers) - 1) cnt[wid][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {
+        uint32_t run = offsets[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+        for (int wv = 0; wv < SORT_WARPS; wv++) {
+            const uint32_t c = cnt[wv][d];
+            cnt[wv][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool live = i < n;
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const uint32_t d = (key[r] >> shift) & (RADIX - 1);
+            const unsigned peers = __match_any_sync(act, d);
+            const uint32_t pos = cnt[wid][d] + __popc(peers & ((1u << lane) - 1));
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+            __syncwarp(act);
+            if (lane == __ffs(peers) - 1) cnt[wid][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+// every sorted position i: compare with its raster-order predecessor in the same target
+__global__ void splat_resolve_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                     const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ winpos,
+                                     uint8_t *__restrict__ warped)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t t = keys[i];
+    if (t >= n) return;  // dropped (out-of-range target)
+    const bool first = (i == 0) || (keys[i - 1] != t);
+    const float zprev = first ? 1000.f : z[vals[i - 1]];  // dlut[t] when this writer arrives (:8-11, :28)
+    if (z[vals[i]] < zprev) atomicMax(&winpos[t], i + 1);  // :19-21, the last such writer wins
+    const bool last = (i + 1 == n) || (keys[i + 1] != t);
+    if (last) {
+        warped[(size_t)t * 5 + 3] = 1;                          // :23
+        warped[(size_t)t * 5 + 4] = (zprev != 1000.f) ? 0 : 1;  // :24-27
+    }
+}
+
+__global__ void splat_rgb_kernel(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ winpos,
+                                 const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ warped)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t wp = winpos[t];
+    if (!wp) return;
+    const uint32_t k = vals[wp - 1];
+    warped[(size_t)t * 5 + 0] = src[(size_t)k * 3 + 0];
+    warped[(size_t)t * 5 + 1] = src[(size_t)k * 3 + 1];
+    warped[(size_t)t * 5 + 2] = src[(size_t)k * 3 + 2];
+}
+
+inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct SplatLayout {
+    size_t keysA, valsA, keysB, valsB, winpos, hist, total;
+    uint32_t nblocks;
+    SplatLayout(size_t n)
+    {
+        nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+        size_t o = 0;
+        keysA = o; o += al256(n * 4);
+        valsA = o; o += al256(n * 4);
+        keysB = o; o += al256(n * 4);
+        valsB = o; o += al256(n * 4);
+        winpos = o; o += al256(n * 4);
+        hist = o; o += al256((size_t)RADIX * nblocks * 4);
+        total = o;
+    }
+};
+
+}  // namespace
+
+MPIFLOW_API size_t mpiflow_forward_warp_workspace_bytes(int h, int w)
+{
+    if (h <= 0 || w <= 0) return 0;
+    return SplatLayout((size_t)h * w).total;
+}
+
+MPIFLOW_API int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx, const int64_t *idy,
+                                         const float *z, uint8_t *warped, int h, int w, void *workspace,
+                                         size_t workspace_bytes, void *stream)
+{
+    if (h == 0 || w == 0) return 0;  // the reference loops zero times
+    MF_CHECK_ARG(src && idx && idy && z && warped && workspace && h > 0 && w > 0);
+    MF_CHECK_ARG((int64_t)h * w < (1ll << 31) && ((uintptr_t)workspace & 255) == 0);
+    const size_t n64 = (size_t)h * w;
+    const SplatLayout L(n64);
+    if (workspace_bytes < L.total) return MPIFLOW_E_WORKSPACE;
+    const uint32_t n = (uint32_t)n64;
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = reinterpret_cast<char *>(workspace);
+    uint32_t *kA = (uint32_t *)(ws + L.keysA), *vA = (uint32_t *)(ws + L.valsA);
+    uint32_t *kB = (uint32_t *)(ws + L.keysB), *vB = (uint32_t *)(ws + L.valsB);
+    uint32_t *winpos = (uint32_t *)(ws + L.winpos), *hist = (uint32_t *)(ws + L.hist);
+    const unsigned g256 = (n + 255) / 256;
+
+    splat_keys_kernel<<<g256, 256, 0, st>>>(idx, idy, h, w, n, kA, vA, winpos);
+    int bits = 0;
+    while ((n >> bits) != 0) bits++;  // keys are in [0, n]
+    for (int shift = 0; shift < bits; shift += RADIX_BITS) {
+        radix_hist_kernel<<<L.nblocks, SORT_THREADS, 0, st>>>(kA, n, shift, L.nblocks, hist);
+        radix_scan_kernel<<<1, 1024, 0, st>>>(hist, RADIX * L.nblocks);
+        radix_scatter_kernel<<<L.nblocks, SORT_THREADS, 0, st>>>(kA, vA, n, shift, L.nblocks, hist, kB, vB);
+        uint32_t *t = kA; kA = kB; kB = t;
+        t = vA; vA = vB; vB = t;
+    }
+    splat_resolve_kernel<<<g256, 256, 0, st>>>(kA, vA, z, n, winpos, warped);
+    splat_rgb_kernel<<<g256, 256, 0, st>>>(vA, winpos, src, n, warped);
+    return mf_launch_status();
+}
+
+// ---- host-pointer entry points ----------------------------------------------------------------
+namespace {
+std::mutex g_host_mu;
+void *g_host_buf = nullptr;
+size_t g_host_cap = 0;
+}  // namespace
+
+MPIFLOW_API int mpiflow_forward_warp_host(const void *src, const void *idx, const void *idy, const void *z,
+                                          void *warped, int h, int w)
+{
+    if (h == 0 || w == 0) return 0;
+    MF_CHECK_ARG(src && idx && idy && z && warped && h > 0 && w > 0 && (int64_t)h * w < (1ll << 31));
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    const size_t n = (size_t)h * w;
+    const size_t o_src = 0, o_idx = al256(n * 3), o_idy = o_idx + al256(n * 8), o_z = o_idy + al256(n * 8);
+    const size_t o_out = o_z + al256(n * 4), o_ws = o_out + al256(n * 5);
+    const size_t ws_bytes = mpiflow_forward_warp_workspace_bytes(h, w), need = o_ws + ws_bytes;
+    cudaError_t e;
+    if (need > g_host_cap) {
+        if (g_host_buf) cudaFree(g_host_buf);
+        g_host_buf = nullptr; g_host_cap = 0;
+        if ((e = cudaMalloc(&g_host_buf, need)) != cudaSuccess) return (int)e;
+        g_host_cap = need;
+    }
+    char *d = reinterpret_cast<char *>(g_host_buf);
+    cudaStream_t st = cudaStreamPerThread;
+    if ((e = cudaMemcpyAsync(d + o_src, src, n * 3, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+    cudaMemcpyAsync(d + o_idx, idx, n * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d + o_idy, idy, n * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d + o_z, z, n * 4, cudaMemcpyHostToDevice, st);
+    // bytes no writer touches keep the caller's content, exactly like the C loop
+    cudaMemcpyAsync(d + o_out, warped, n * 5, cudaMemcpyHostToDevice, st);
+    int rc = mpiflow_forward_warp_f32((const uint8_t *)(d + o_src), (const int64_t *)(d + o_idx),
+                                      (const int64_t *)(d + o_idy), (const float *)(d + o_z),
+                                      (uint8_t *)(d + o_out), h, w, d + o_ws, ws_bytes, st);
+    if (rc) return rc;
+    if ((e = cudaMemcpyAsync(warped, d + o_out, n * 5, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+    return (int)cudaStreamSynchronize(st);
+}
+
+// legacy symbol: external/forward_warping/warping.c:6 (void return, no error reporting)
+MPIFLOW_API void forward_warping(const void *src, const void *idx, const void *idy, const void *z,
+                                 void *warped, int h, int w)
+{
+    const int rc = mpiflow_forward_warp_host(src, idx, idy, z, warped, h, w);
+    if (rc != 0) {
+        // the reference cannot fail; a GPU failure must not pass silently as an all-zero image
+        fprintf(stderr, "forward_warping (libmpiflow_sm100): %s (code %d)\n", mpiflow_error_string(rc), rc);
+        abort();
+    }
+}

@@ -137,3 +137,23 @@ def test_known_answers():
     for s in range(4):
         assert np.abs(fl[s, :, :, 0] - fx * 0.1 / depth_s[s]).max() <= 1e-4
         assert np.abs(fl[s, :, :, 1]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["frame_white_random", "frame_smooth_regression", "frame_object_pose_flags"])
+def test_torch_ref_matches_reference(golden_dir, name):
+    """oracle/torch_ref.py (the library-operator restatement used on the GPU box) against the
+    reference's own CPU outputs."""
+    import torch
+    from oracle import torch_ref
+    g = load(golden_dir, name)
+    inp = frame_inputs_of(g)
+    T = torch.from_numpy
+    out = torch_ref.render_frame(T(inp["mpi"]), T(inp["disparity"]), T(inp["G"]), T(inp["Kinv"]), T(inp["K"]),
+                                 T(inp["obj_mask"]), is_bg_depth_inf=bool(g["is_bg_depth_inf"]),
+                                 hard_flow=bool(g["hard_flow"]))
+    rgb, depth, mask, flow, obj = (o.numpy() for o in out)
+    assert np.abs(rgb - g["out_rgb"]).max() <= 2e-6
+    assert np.abs(flow - g["out_flow"]).max() <= 2e-6
+    assert np.abs(obj - g["out_obj"]).max() <= 2e-6
+    np.testing.assert_array_equal(mask, g["out_mask"])
+    np.testing.assert_allclose(depth, g["out_depth"], rtol=1e-5, atol=1e-5)
