@@ -72,6 +72,10 @@ int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, i
                              float *out_obj, void *workspace, size_t workspace_bytes, int *status,
                              void *stream);
 
+/* test hook: the shared-reciprocal IEEE division of the kernels, element-wise: qa = a/b, qc = c/b */
+int mpiflow_debug_div_f32(const float *a, const float *c, const float *b, int n, float *qa, float *qc,
+                          void *stream);
+
 /* Same computation from HOST buffers (dense layouts: mpi [B,S,4,H,W] = rgb+sigma, obj [B,1,H,W]):
  * H2D of the inputs, the two launches, D2H of the five outputs, all inside the call; returns
  * MPIFLOW_E_SINGULAR like the reference raises.  Frames are pipelined over two streams. */

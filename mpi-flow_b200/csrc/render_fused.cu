@@ -12,23 +12,16 @@
 // the whole plane loop; nothing of size [B,S,*,H,W] is ever written.
 //
 // Algorithmic HBM bytes per frame: 4*H*W*(4S + 1 + 8)   (RGBA once, mask once, 8 output channels).
-#include "homography.cuh"
+#include <cstdlib>
+#include <cstring>
 
-struct RenderParams {
-    const float *rgb;   int64_t rgb_sb, rgb_ss, rgb_sc;
-    const float *sigma; int64_t sig_sb, sig_ss;
-    const float *obj;   int64_t obj_sb, obj_ss;
-    const PlaneConst *pc;  // [B*S]
-    const float *Kinv;     // [B,3,3]
-    int B, S, H, W;
-    unsigned flags;
-    float *out_rgb, *out_depth, *out_mask, *out_flow, *out_obj;
-};
+#include "render_tma.cuh"
 
 // prologue: PlaneConst for every (b, s); inputs are per batch.
 __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__restrict__ Kinv,
                                     const float *__restrict__ Kt, const float *__restrict__ disparity,
-                                    int B, int S, PlaneConst *__restrict__ pc, int *__restrict__ status)
+                                    int B, int S, PlaneConst *__restrict__ pc, BatchConst *__restrict__ bcs,
+                                    int *__restrict__ status)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= B * S) return;
@@ -50,9 +43,22 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
     for (int i = 0; i < 3; i++) c.P[i * 3 + 2] = __fadd_rn(c.P[i * 3 + 2], g[i * 4 + 3]);
     c.depth = depth;
     c.ddepth = (s + 1 < S) ? __fsub_rn(__frcp_rn(disparity[n + 1]), depth) : 0.f;
-    c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
+    c.ddepth_l2e = c.ddepth * 1.4426950408889634f;
+    c.pad[0] = c.pad[1] = 0.f;
     pc[n] = c;
-    if (!ok && status) atomicExch(status, 1);
+    bool okb = true;
+    if (s == 0) {
+        BatchConst bc;
+        double k64[9], ki64[9];
+        for (int i = 0; i < 9; i++) { bc.kinv[i] = ki[i]; k64[i] = (double)kt[i]; }
+        okb = inverse33_f64(k64, ki64);
+        for (int i = 0; i < 9; i++) bc.ktinv[i] = okb ? (float)ki64[i] : 0.f;
+        for (int i = 0; i < 3; i++) bc.rt2[i] = g[i * 4 + 2];
+        bc.a = fmaf(g[2 * 4 + 2], g[2 * 4 + 3], fmaf(g[1 * 4 + 2], g[1 * 4 + 3], g[0 * 4 + 2] * g[0 * 4 + 3]));
+        bc.pad[0] = bc.pad[1] = 0.f;
+        bcs[b] = bc;
+    }
+    if (!(ok && okb) && status) atomicExch(status, 1);
 }
 
 // front-to-back accumulator of one frame (mpi_rendering.py:79-96, :143-152)
@@ -99,7 +105,7 @@ render_fused_kernel(const RenderParams p)
     // the spacing of consecutive planes along it is |ray| * (depth[s+1] - depth[s])   (:104-107)
     float vnorm;
     {
-        const float *k = p.Kinv + (size_t)b * 9;
+        const float *k = p.bc[b].kinv;
         const float v0 = mf_dot3(__ldg(k + 0), __ldg(k + 1), __ldg(k + 2), xf, yf);
         const float v1 = mf_dot3(__ldg(k + 3), __ldg(k + 4), __ldg(k + 5), xf, yf);
         const float v2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
@@ -192,7 +198,97 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 MPIFLOW_API size_t mpiflow_render_workspace_bytes(int B, int S)
 {
     if (B <= 0 || S <= 0) return 0;
-    return align_up((size_t)B * S * sizeof(PlaneConst), 256) + 256;
+    return align_up((size_t)B * S * sizeof(PlaneConst), 256) + align_up((size_t)B * sizeof(BatchConst), 256) + 256;
+}
+
+// ---- TMA path ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// fp32 tensor map over (W, H, d2[, d3[, d4]]) with byte strides; box (bw, bh, b2, 1, 1)
+static bool make_map(CUtensorMap *m, const float *ptr, int rank, const uint64_t *dims, const uint64_t *strides_b,
+                     uint32_t bw, uint32_t bh, uint32_t b2)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t box[5] = {bw, bh, b2, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < rank; i++) gd[i] = dims[i];
+    for (int i = 0; i < rank - 1; i++) {
+        gs[i] = strides_b[i];
+        if (gs[i] % 16 != 0 || gs[i] == 0) return false;
+    }
+    if (((uintptr_t)ptr & 15) != 0) return false;
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)ptr, gd, gs, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <class Cfg>
+static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
+{
+    *used = false;
+    const int B = p.B, S = p.S, H = p.H, W = p.W;
+    const size_t smem = Cfg::smem_bytes(S);
+    if (smem > 227 * 1024 || (W % 4) != 0) return 0;
+    const uint64_t w4 = (uint64_t)W * 4, hw4 = (uint64_t)H * W * 4;
+    CUtensorMap m_rgb, m_sig, m_obj;
+    {
+        const uint64_t d[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)S, (uint64_t)B};
+        const uint64_t sb[4] = {w4, (uint64_t)p.rgb_sc * 4, (uint64_t)(S > 1 ? p.rgb_ss : p.rgb_sc * 3) * 4,
+                                (uint64_t)(B > 1 ? p.rgb_sb : (int64_t)hw4) * (B > 1 ? 4 : 1)};
+        if (p.rgb_sc <= 0 || p.rgb_ss < 0 || p.rgb_sb < 0) return 0;
+        if (!make_map(&m_rgb, p.rgb, 5, d, sb, Cfg::BW, Cfg::BH, 3)) return 0;
+    }
+    {
+        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+        const uint64_t sb[3] = {w4, (uint64_t)(S > 1 ? p.sig_ss * 4 : (int64_t)hw4), (uint64_t)(B > 1 ? p.sig_sb * 4 : (int64_t)hw4)};
+        if (p.sig_ss < 0 || p.sig_sb < 0) return 0;
+        if (!make_map(&m_sig, p.sigma, 4, d, sb, Cfg::BW, Cfg::BH, 1)) return 0;
+    }
+    if (p.obj) {
+        const bool shared_mask = (p.obj_ss == 0) || S == 1;
+        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)(shared_mask ? 1 : S), (uint64_t)B};
+        const uint64_t sb[3] = {w4, (uint64_t)(shared_mask ? (int64_t)hw4 : p.obj_ss * 4), (uint64_t)(B > 1 ? p.obj_sb * 4 : (int64_t)hw4)};
+        if (p.obj_ss < 0 || p.obj_sb < 0) return 0;
+        if (!make_map(&m_obj, p.obj, 4, d, sb, Cfg::BW, Cfg::BH, 1)) return 0;
+    } else {
+        m_obj = m_sig;
+    }
+    auto kern = p.obj ? render_fused_tma_kernel<Cfg, true> : render_fused_tma_kernel<Cfg, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((W + Cfg::TW - 1) / Cfg::TW, (H + Cfg::TH - 1) / Cfg::TH, B);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(m_rgb, m_sig, m_obj, p);
+    *used = true;
+    return mf_launch_status();
+}
+
+// tile 64x16, box 80x24, 4-stage ring, 2 pixels per thread: 153.6 KB of stages, 1 CTA / SM
+typedef TmaCfg<64, 16, 80, 24, 4, 2> CfgDefault;
+
+// MPIFLOW_RENDER_PATH=generic forces the plain global-load kernel (debugging / A-B measurements)
+static bool tma_enabled()
+{
+    static const bool on = []() {
+        const char *v = getenv("MPIFLOW_RENDER_PATH");
+        return !(v && strcmp(v, "generic") == 0);
+    }();
+    return on;
 }
 
 MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
@@ -218,7 +314,9 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
         if (e != cudaSuccess) return (int)e;
     }
     PlaneConst *pc = reinterpret_cast<PlaneConst *>(workspace);
-    plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, status);
+    BatchConst *bc = reinterpret_cast<BatchConst *>(reinterpret_cast<char *>(workspace) +
+                                                    align_up((size_t)B * S * sizeof(PlaneConst), 256));
+    plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, bc, status);
     int rc = mf_launch_status();
     if (rc) return rc;
 
@@ -226,10 +324,17 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     p.rgb = rgb; p.rgb_sb = rgb_sb; p.rgb_ss = rgb_ss; p.rgb_sc = rgb_sc;
     p.sigma = sigma; p.sig_sb = sig_sb; p.sig_ss = sig_ss;
     p.obj = obj; p.obj_sb = obj_sb; p.obj_ss = obj_ss;
-    p.pc = pc; p.Kinv = Kinv;
+    p.pc = pc; p.bc = bc;
     p.B = B; p.S = S; p.H = H; p.W = W; p.flags = flags;
     p.out_rgb = out_rgb; p.out_depth = out_depth; p.out_mask = out_mask; p.out_flow = out_flow;
     p.out_obj = out_obj;
+
+    if (tma_enabled()) {
+        bool used = false;
+        rc = launch_tma<CfgDefault>(p, st, &used);
+        if (rc || used) return rc;
+    }
+    // generic path: tensors TMA cannot describe (W % 4 != 0, unaligned base, odd strides)
     dim3 grid((W + 31) / 32, (H + 7) / 8, B);
     auto kern = obj ? render_fused_kernel<true> : render_fused_kernel<false>;
     if (smem > 48 * 1024) {
@@ -237,5 +342,20 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
         if (e != cudaSuccess) return (int)e;
     }
     kern<<<grid, 256, smem, st>>>(p);
+    return mf_launch_status();
+}
+
+// test hook: the shared-reciprocal division used in the kernels, element-wise on device arrays
+__global__ void debug_div_kernel(const float *a, const float *c, const float *b, int n, float *qa, float *qc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mf_div2(a[i], c[i], b[i], qa[i], qc[i]);
+}
+
+MPIFLOW_API int mpiflow_debug_div_f32(const float *a, const float *c, const float *b, int n, float *qa, float *qc,
+                                      void *stream)
+{
+    MF_CHECK_ARG(a && c && b && qa && qc && n > 0);
+    debug_div_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, c, b, n, qa, qc);
     return mf_launch_status();
 }

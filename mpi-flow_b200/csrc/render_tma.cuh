@@ -1,0 +1,372 @@
+// render_tma.cuh -- TMA-staged variant of the fused MPI renderer (sm_100a).
+//
+// CTA = one TW x TH tile of pixel indices of one batch entry.  For every plane s warp 0 (which also
+// renders) maps the tile corners through H_src_tgt(s) (same arithmetic as the pixels), derives the
+// source footprint, and issues three cp.async.bulk.tensor loads (rgb x3, sigma, object mask) of a
+// fixed BW x BH box around it into a STAGES-deep shared-memory ring guarded by full/empty mbarriers.
+// Consumer warps (PPT pixels per thread, same column, rows TH/PPT apart) take their four bilinear
+// taps per channel from shared memory with immediate offsets, so the plane loop has no 64-bit address
+// arithmetic and HBM/L2 latency is hidden by the ring instead of by occupancy.
+// A plane whose footprint does not fit the box (strong zoom / degenerate pose) is read with plain
+// global loads for that (tile, plane) only -- results are identical.
+#pragma once
+#include <cuda.h>
+
+#include "homography.cuh"
+
+struct RenderParams {
+    const float *rgb;   int64_t rgb_sb, rgb_ss, rgb_sc;
+    const float *sigma; int64_t sig_sb, sig_ss;
+    const float *obj;   int64_t obj_sb, obj_ss;
+    const PlaneConst *pc;  // [B*S]
+    const BatchConst *bc;  // [B]
+    int B, S, H, W;
+    unsigned flags;
+    float *out_rgb, *out_depth, *out_mask, *out_flow, *out_obj;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ float fast_sqrt(float v)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_ex2(float v)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// ---- per-pixel state ---------------------------------------------------------------------------------
+// front-to-back accumulators of one pixel (mpi_rendering.py:79-96, :143-152) plus the plane that is
+// still waiting for its successor's geometry (its thickness is |xyz[s+1] - xyz[s]|, :68-71)
+struct PixelState {
+    float acc, r, g, b, zsum, wsum, obj, cnt;  // target frame
+    float pr, pg, pb, psig, pm, pz;            // pending plane s-1
+    float pix, piy;                            // its clamped sample position
+    bool pclamped;
+    float acc_s, fu, fv, best_w;               // source frame
+};
+
+template <int TW_, int TH_, int BW_, int BH_, int STAGES_, int PPT_>
+struct TmaCfg {
+    static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_, STAGES = STAGES_, PPT = PPT_;
+    static constexpr int ROWS = TH / PPT;                 // rows per pass
+    static constexpr int CONSUMER_WARPS = (TW / 32) * ROWS;
+    static constexpr int CONSUMERS = CONSUMER_WARPS * 32;
+    static constexpr int THREADS = CONSUMERS;             // warp 0 doubles as the TMA producer
+    static constexpr int CH_FLOATS = BW * BH;             // one channel of one stage
+    static constexpr int STAGE_FLOATS = 5 * CH_FLOATS;    // r,g,b,sigma,obj
+    static constexpr size_t STAGE_BYTES = (size_t)STAGE_FLOATS * sizeof(float);
+    static_assert(TW % 32 == 0 && TH % PPT == 0 && BW % 4 == 0, "tile shape");
+    static_assert((CH_FLOATS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static size_t smem_bytes(int S)
+    {
+        return 128 /*alignment slack*/ + STAGES * STAGE_BYTES + (size_t)S * sizeof(PlaneConst) + 2 * STAGES * 8 + STAGES * 16;
+    }
+};
+
+template <class Cfg, bool HAS_OBJ>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __grid_constant__ CUtensorMap map_sig,
+                        const __grid_constant__ CUtensorMap map_obj, const RenderParams p)
+{
+    constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH, STAGES = Cfg::STAGES, PPT = Cfg::PPT;
+    constexpr int CH = Cfg::CH_FLOATS;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    float *stage_buf = reinterpret_cast<float *>(base);
+    PlaneConst *spc = reinterpret_cast<PlaneConst *>(base + STAGES * Cfg::STAGE_BYTES);
+    const int S = p.S, H = p.H, W = p.W;
+    uint64_t *full = reinterpret_cast<uint64_t *>(spc + S);
+    uint64_t *empty = full + STAGES;
+    int4 *meta = reinterpret_cast<int4 *>(empty + STAGES);  // {bx, by, fits, -}
+
+    const int b = blockIdx.z;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    {   // plane constants of this batch entry + barrier init
+        const float4 *src = reinterpret_cast<const float4 *>(p.pc + (size_t)b * S);
+        float4 *dst = reinterpret_cast<float4 *>(spc);
+        for (int i = threadIdx.x; i < S * 8; i += Cfg::THREADS) dst[i] = __ldg(src + i);
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < STAGES; i++) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], Cfg::CONSUMER_WARPS);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
+    const float Wf = (float)W, Hf = (float)H;
+    const float rW = __frcp_rn(Wf * 0.5f), rH = __frcp_rn(Hf * 0.5f);
+
+    // ---- producer role (warp 0): footprint of plane sl for this tile -> TMA into stage sl % STAGES ----
+    // lanes 0..3 own the four (clamped-to-image) corners of the tile
+    const int cx = min(tx0 + ((lane & 1) ? TW - 1 : 0), W - 1);
+    const int cy = min(ty0 + ((lane & 2) ? TH - 1 : 0), H - 1);
+    auto produce = [&](int sl) {
+        const int st = sl % STAGES;
+        const PlaneConst &c = spc[sl];
+        const SrcPos sp = tgt_to_src(c.hst, (float)cx, (float)cy, Wf, Hf, rW, rH);
+        const float Zc = mf_dot3(c.hst[6], c.hst[7], c.hst[8], (float)cx, (float)cy);
+        float mnx = sp.ix, mxx = sp.ix, mny = sp.iy, mxy = sp.iy;
+        int ok = (Zc > 0.f) && (sp.ix == sp.ix) && (sp.iy == sp.iy);
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+            ok &= __shfl_xor_sync(0xffffffffu, ok, o);
+        }
+        if (lane == 0) {
+            // 0.02 px of slack covers fp32 rounding of interior pixels relative to the corners
+            // TMA needs a 16-byte aligned box start in the innermost dimension: round x down to 4 texels
+            const int bx = ((int)floorf(mnx - 0.02f)) & ~3, by = (int)floorf(mny - 0.02f);
+            const int ex = (int)floorf(mxx + 0.02f) + 1, ey = (int)floorf(mxy + 0.02f) + 1;  // last tap col/row
+            const bool fits = ok && (ex - bx + 1 <= BW) && (ey - by + 1 <= BH);
+            meta[st] = make_int4(bx, by, fits ? 1 : 0, 0);
+            if (fits) {
+                float *dst = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
+                mbar_arrive_expect_tx(&full[st], (HAS_OBJ ? 5 : 4) * CH * (uint32_t)sizeof(float));
+                tma_load_5d(dst, &map_rgb, &full[st], bx, by, 0, sl, b);
+                tma_load_4d(dst + 3 * CH, &map_sig, &full[st], bx, by, sl, b);
+                if (HAS_OBJ) tma_load_4d(dst + 4 * CH, &map_obj, &full[st], bx, by, p.obj_ss ? sl : 0, b);
+            } else {
+                mbar_arrive(&full[st]);
+            }
+        }
+        __syncwarp();
+    };
+    if (warp == 0)
+        for (int sl = 0; sl < STAGES - 1 && sl < S; sl++) produce(sl);
+
+    const int xi = min(tx0 + (warp % (TW / 32)) * 32 + lane, W - 1);  // clamped: out-of-image threads
+    const int row0 = warp / (TW / 32);                                // recompute a border pixel
+    const float xf = (float)xi;
+    const BatchConst &bc = p.bc[b];
+    const size_t HW = (size_t)H * W;
+    const float *rgb_b = p.rgb + (size_t)b * p.rgb_sb;
+    const float *sig_b = p.sigma + (size_t)b * p.sig_sb;
+    const float *obj_b = HAS_OBJ ? p.obj + (size_t)b * p.obj_sb : nullptr;
+    const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
+
+    int yi[PPT];
+    float yf[PPT], vnorm[PPT], tdist[PPT], invb[PPT];
+    PixelState ps[PPT];
+    float sig_next[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        yi[j] = min(ty0 + row0 + j * Cfg::ROWS, H - 1);
+        yf[j] = (float)yi[j];
+        // source-frame ray |Kinv (x,y,1)|: spacing of planes s, s+1 along it = vnorm * (d[s+1]-d[s])
+        const float v0 = mf_dot3(bc.kinv[0], bc.kinv[1], bc.kinv[2], xf, yf[j]);
+        const float v1 = mf_dot3(bc.kinv[3], bc.kinv[4], bc.kinv[5], xf, yf[j]);
+        const float v2 = mf_dot3(bc.kinv[6], bc.kinv[7], bc.kinv[8], xf, yf[j]);
+        vnorm[j] = sqrtf(fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
+        // target-frame ray r = Kt^-1 (x,y,1); plane s is hit at depth Z_s = (d_s + a) / b(q) with
+        // a = (R^T t)_z, b(q) = (R^T r)_z; consecutive hits are |r| |d[s+1]-d[s]| / |b| apart
+        const float r0 = mf_dot3(bc.ktinv[0], bc.ktinv[1], bc.ktinv[2], xf, yf[j]);
+        const float r1 = mf_dot3(bc.ktinv[3], bc.ktinv[4], bc.ktinv[5], xf, yf[j]);
+        const float r2 = mf_dot3(bc.ktinv[6], bc.ktinv[7], bc.ktinv[8], xf, yf[j]);
+        const float bq = fmaf(bc.rt2[2], r2, fmaf(bc.rt2[1], r1, bc.rt2[0] * r0));
+        invb[j] = __frcp_rn(bq);
+        tdist[j] = sqrtf(fmaf(r2, r2, fmaf(r1, r1, r0 * r0))) * fabsf(invb[j]);
+        PixelState &q = ps[j];
+        q.acc = 1.f; q.r = q.g = q.b = q.zsum = q.wsum = q.obj = q.cnt = 0.f;
+        q.pr = q.pg = q.pb = q.psig = q.pm = q.pz = q.pix = q.piy = 0.f;
+        q.pclamped = false;
+        q.acc_s = 1.f; q.fu = q.fv = 0.f; q.best_w = -1.f;
+        sig_next[j] = __ldg(sig_b + (size_t)yi[j] * W + xi);
+    }
+
+    // composite plane s-1 once plane s's geometry is known
+    auto composite = [&](PixelState &q, float dist) {
+        const float T = fast_ex2(-q.psig * dist);  // dist carries log2(e)
+        const float w = q.acc * (1.f - T);
+        q.acc *= (T + 1e-6f);
+        q.wsum += w;
+        q.r = fmaf(w, q.pr, q.r);
+        q.g = fmaf(w, q.pg, q.g);
+        q.b = fmaf(w, q.pb, q.b);
+        q.zsum = fmaf(w, q.pz, q.zsum);
+        if (HAS_OBJ) q.obj = fmaf(w, q.pm, q.obj);
+    };
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    for (int s = 0; s < S; s++) {
+        const int st = s % STAGES;
+        if (warp == 0 && s + STAGES - 1 < S) {
+            // the stage plane s-1 used is free once every warp has arrived on its empty barrier
+            if (s >= 1) mbar_wait(&empty[(s - 1) % STAGES], ((s - 1) / STAGES) & 1);
+            produce(s + STAGES - 1);
+        }
+        const PlaneConst &c = spc[s];
+        const float *sm = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
+        mbar_wait(&full[st], (s / STAGES) & 1);
+        const int4 mt = meta[st];
+        const bool last = (s + 1 == S);
+        const float zc = c.depth + bc.a;  // numerator of Z_s
+        // shared by the PPT pixels of this thread (same column): first product of each FMA chain
+        const float hx0 = __fmul_rn(c.hst[0], xf), hx3 = __fmul_rn(c.hst[3], xf), hx6 = __fmul_rn(c.hst[6], xf);
+        const float gx0 = __fmul_rn(c.hts[0], xf), gx3 = __fmul_rn(c.hts[3], xf), gx6 = __fmul_rn(c.hts[6], xf);
+        const float *sig_s = sig_b + (size_t)s * p.sig_ss;
+#pragma unroll
+        for (int j = 0; j < PPT; j++) {
+            PixelState &q = ps[j];
+            // ---------------- target frame: position ----------------
+            const float X = __fadd_rn(__fmaf_rn(c.hst[1], yf[j], hx0), c.hst[2]);
+            const float Y = __fadd_rn(__fmaf_rn(c.hst[4], yf[j], hx3), c.hst[5]);
+            const float Z = __fadd_rn(__fmaf_rn(c.hst[7], yf[j], hx6), c.hst[8]);
+            float sx, sy;
+            mf_div2(X, Y, Z, sx, sy);
+            const bool valid = (sx < Wf) && (sx > -1.f) && (sy < Hf) && (sy > -1.f);
+            q.cnt += valid ? 1.f : 0.f;
+            const float gx = __fadd_rn(__fmul_rn(__fadd_rn(sx, 0.5f), rW), -1.f);
+            const float gy = __fadd_rn(__fmul_rn(__fadd_rn(sy, 0.5f), rH), -1.f);
+            const float ixu = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), Wf, -1.f), 0.5f);
+            const float iyu = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), Hf, -1.f), 0.5f);
+            const float ix = fminf(Wf - 1.f, fmaxf(ixu, 0.f));
+            const float iy = fminf(Hf - 1.f, fmaxf(iyu, 0.f));
+            const bool clamped = (ix != ixu) || (iy != iyu);
+            const float x0f = floorf(ix), y0f = floorf(iy);
+            const float wx1 = __fsub_rn(__fadd_rn(x0f, 1.f), ix), wx0 = __fsub_rn(ix, x0f);
+            const float wy1 = __fsub_rn(__fadd_rn(y0f, 1.f), iy), wy0 = __fsub_rn(iy, y0f);
+            const float nw = __fmul_rn(wx1, wy1), ne = __fmul_rn(wx0, wy1);
+            const float sw = __fmul_rn(wx1, wy0), se = __fmul_rn(wx0, wy0);
+            const int x0 = (int)x0f, y0 = (int)y0f;
+            float cr, cg, cb, sg, m = 0.f;
+            if (mt.z) {  // warp-uniform: the plane's footprint is in shared memory
+                const float *t = sm + (y0 - mt.y) * BW + (x0 - mt.x);
+                auto tap = [&](const float *u) {
+                    float a = __fmul_rn(u[0], nw);
+                    a = __fmaf_rn(u[1], ne, a);
+                    a = __fmaf_rn(u[BW], sw, a);
+                    return __fmaf_rn(u[BW + 1], se, a);
+                };
+                cr = tap(t); cg = tap(t + CH); cb = tap(t + 2 * CH); sg = tap(t + 3 * CH);
+                if (HAS_OBJ) m = tap(t + 4 * CH);
+            } else {     // same taps straight from global memory
+                const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+                const int o00 = y0 * W + x0, o01 = y0 * W + x1, o10 = y1 * W + x0, o11 = y1 * W + x1;
+                auto tap = [&](const float *img) {
+                    float a = __fmul_rn(__ldg(img + o00), nw);
+                    a = __fmaf_rn(__ldg(img + o01), ne, a);
+                    a = __fmaf_rn(__ldg(img + o10), sw, a);
+                    return __fmaf_rn(__ldg(img + o11), se, a);
+                };
+                const float *rgb_s = rgb_b + (size_t)s * p.rgb_ss;
+                cr = tap(rgb_s); cg = tap(rgb_s + p.rgb_sc); cb = tap(rgb_s + 2 * p.rgb_sc);
+                sg = tap(sig_s);
+                if (HAS_OBJ) m = tap(obj_b + (size_t)s * p.obj_ss);
+            }
+            // ---------------- target frame: geometry + composite of plane s-1 ----------------
+            float Zt;
+            if (!(clamped || q.pclamped)) {
+                Zt = zc * invb[j];
+                if (s > 0) composite(q, tdist[j] * spc[s - 1].ddepth_l2e);
+            } else {
+                // a clamped sample leaves the pixel's ray: evaluate xyz_tgt at the clamped positions
+                const float Xc = fmaf(c.P[0], ix, fmaf(c.P[1], iy, c.P[2]));
+                const float Yc = fmaf(c.P[3], ix, fmaf(c.P[4], iy, c.P[5]));
+                Zt = fmaf(c.P[6], ix, fmaf(c.P[7], iy, c.P[8]));
+                if (s > 0) {
+                    const PlaneConst &cp = spc[s - 1];
+                    const float Xp = fmaf(cp.P[0], q.pix, fmaf(cp.P[1], q.piy, cp.P[2]));
+                    const float Yp = fmaf(cp.P[3], q.pix, fmaf(cp.P[4], q.piy, cp.P[5]));
+                    const float Zp = fmaf(cp.P[6], q.pix, fmaf(cp.P[7], q.piy, cp.P[8]));
+                    const float dx = Xc - Xp, dy = Yc - Yp, dz = Zt - Zp;
+                    q.pz = Zp;
+                    composite(q, fast_sqrt(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * LOG2E);
+                }
+            }
+            q.pr = cr; q.pg = cg; q.pb = cb; q.pm = m; q.pz = Zt;
+            q.psig = (Zt >= 0.f) ? sg : 0.f;  // :334-338
+            q.pix = ix; q.piy = iy; q.pclamped = clamped;
+
+            // ---------------- source frame ----------------
+            const float U = __fadd_rn(__fmaf_rn(c.hts[1], yf[j], gx0), c.hts[2]);
+            const float V = __fadd_rn(__fmaf_rn(c.hts[4], yf[j], gx3), c.hts[5]);
+            const float Q = __fadd_rn(__fmaf_rn(c.hts[7], yf[j], gx6), c.hts[8]);
+            float tu, tv;
+            mf_div2(U, V, Q, tu, tv);
+            const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf[j]);  // :212-218
+            const float sgs = sig_next[j];
+            if (!last) sig_next[j] = __ldg(sig_s + p.sig_ss + (size_t)yi[j] * W + xi);  // prefetch plane s+1
+            const float Ts = fast_ex2(-sgs * (last ? 1e3f * LOG2E : vnorm[j] * c.ddepth_l2e));
+            const float ws = q.acc_s * (1.f - Ts);
+            q.acc_s *= (Ts + 1e-6f);
+            if (hard) {
+                if (ws > q.best_w) { q.best_w = ws; q.fu = du; q.fv = dv; }
+            } else {
+                q.fu = fmaf(ws, du, q.fu);
+                q.fv = fmaf(ws, dv, q.fv);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+    }
+
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+        PixelState &q = ps[j];
+        composite(q, 1e3f * LOG2E);  // last plane: thickness 1e3 (:73-78)
+        const int x = tx0 + (warp % (TW / 32)) * 32 + lane, y = ty0 + row0 + j * Cfg::ROWS;
+        if (x >= W || y >= H) continue;
+        const size_t o = (size_t)y * W + x;
+        float *orgb = p.out_rgb + (size_t)b * 3 * HW + o;
+        orgb[0] = q.r; orgb[HW] = q.g; orgb[2 * HW] = q.b;
+        p.out_depth[(size_t)b * HW + o] = (p.flags & MPIFLOW_BG_DEPTH_INF) ? fmaf(1.f - q.wsum, 1000.f, q.zsum)
+                                                                           : __fdiv_rn(q.zsum, q.wsum + 1e-5f);
+        p.out_mask[(size_t)b * HW + o] = q.cnt;
+        p.out_flow[(size_t)b * 2 * HW + o] = q.fu;
+        p.out_flow[(size_t)b * 2 * HW + HW + o] = q.fv;
+        if (HAS_OBJ && p.out_obj) p.out_obj[(size_t)b * HW + o] = q.obj;
+    }
+}
