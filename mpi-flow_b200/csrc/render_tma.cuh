@@ -115,10 +115,11 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
 {
     constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH, STAGES = Cfg::STAGES, PPT = Cfg::PPT;
     constexpr int CH = Cfg::CH_FLOATS;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    float *stage_buf = reinterpret_cast<float *>(base);
-    PlaneConst *spc = reinterpret_cast<PlaneConst *>(base + STAGES * Cfg::STAGE_BYTES);
+    // no integer round-trip on the pointer: the compiler must keep seeing the shared address space
+    // (generic LD instead of LDS otherwise); TMA needs the 128-byte alignment, checked below
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *stage_buf = reinterpret_cast<float *>(smem_raw);
+    PlaneConst *spc = reinterpret_cast<PlaneConst *>(smem_raw + STAGES * Cfg::STAGE_BYTES);
     const int S = p.S, H = p.H, W = p.W;
     uint64_t *full = reinterpret_cast<uint64_t *>(spc + S);
     uint64_t *empty = full + STAGES;
@@ -133,6 +134,7 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
         float4 *dst = reinterpret_cast<float4 *>(spc);
         for (int i = threadIdx.x; i < S * 8; i += Cfg::THREADS) dst[i] = __ldg(src + i);
         if (threadIdx.x == 0) {
+            if (smem_u32(smem_raw) & 127u) __trap();
             for (int i = 0; i < STAGES; i++) {
                 mbar_init(&full[i], 1);
                 mbar_init(&empty[i], Cfg::CONSUMER_WARPS);
@@ -250,6 +252,15 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
         const PlaneConst &c = spc[s];
         const float *sm = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
         mbar_wait(&full[st], (s / STAGES) & 1);
+        // un-warped sigma of the NEXT plane for the source-frame weights: issued now (asm volatile keeps
+        // it here), consumed one iteration later, so its L2 latency hides behind this plane's work
+        float sig_pref[PPT];
+        {
+            const float *sn = sig_b + (size_t)min(s + 1, S - 1) * p.sig_ss;
+#pragma unroll
+            for (int j = 0; j < PPT; j++)
+                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(sig_pref[j]) : "l"(sn + (size_t)yi[j] * W + xi));
+        }
         const int4 mt = meta[st];
         const bool last = (s + 1 == S);
         const float zc = c.depth + bc.a;  // numerator of Z_s
@@ -338,7 +349,6 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
             mf_div2(U, V, Q, tu, tv);
             const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf[j]);  // :212-218
             const float sgs = sig_next[j];
-            if (!last) sig_next[j] = __ldg(sig_s + p.sig_ss + (size_t)yi[j] * W + xi);  // prefetch plane s+1
             const float Ts = fast_ex2(-sgs * (last ? 1e3f * LOG2E : vnorm[j] * c.ddepth_l2e));
             const float ws = q.acc_s * (1.f - Ts);
             q.acc_s *= (Ts + 1e-6f);
@@ -351,6 +361,8 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
+#pragma unroll
+        for (int j = 0; j < PPT; j++) sig_next[j] = sig_pref[j];
     }
 
 #pragma unroll
