@@ -83,7 +83,7 @@ template <bool HAS_OBJ>
 __global__ void __launch_bounds__(256)
 render_fused_kernel(const RenderParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     PlaneConst *spc = reinterpret_cast<PlaneConst *>(smem_raw);
     const int b = blockIdx.z;
     const int S = p.S, H = p.H, W = p.W;
@@ -246,7 +246,7 @@ static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
     const size_t smem = Cfg::smem_bytes(S);
     if (smem > 227 * 1024 || (W % 4) != 0) return 0;
     const uint64_t w4 = (uint64_t)W * 4, hw4 = (uint64_t)H * W * 4;
-    CUtensorMap m_rgb, m_sig, m_obj;
+    CUtensorMap m_rgb, m_sig, m_obj, m_sigd;
     {
         const uint64_t d[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)S, (uint64_t)B};
         const uint64_t sb[4] = {w4, (uint64_t)p.rgb_sc * 4, (uint64_t)(S > 1 ? p.rgb_ss : p.rgb_sc * 3) * 4,
@@ -259,6 +259,7 @@ static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
         const uint64_t sb[3] = {w4, (uint64_t)(S > 1 ? p.sig_ss * 4 : (int64_t)hw4), (uint64_t)(B > 1 ? p.sig_sb * 4 : (int64_t)hw4)};
         if (p.sig_ss < 0 || p.sig_sb < 0) return 0;
         if (!make_map(&m_sig, p.sigma, 4, d, sb, Cfg::BW, Cfg::BH, 1)) return 0;
+        if (!make_map(&m_sigd, p.sigma, 4, d, sb, Cfg::TW, Cfg::TH, 1)) return 0;
     }
     if (p.obj) {
         const bool shared_mask = (p.obj_ss == 0) || S == 1;
@@ -269,17 +270,32 @@ static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
     } else {
         m_obj = m_sig;
     }
-    auto kern = p.obj ? render_fused_tma_kernel<Cfg, true> : render_fused_tma_kernel<Cfg, false>;
+    const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
+    auto kern = p.obj ? (hard ? render_fused_tma_kernel<Cfg, true, true> : render_fused_tma_kernel<Cfg, true, false>)
+                      : (hard ? render_fused_tma_kernel<Cfg, false, true> : render_fused_tma_kernel<Cfg, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((W + Cfg::TW - 1) / Cfg::TW, (H + Cfg::TH - 1) / Cfg::TH, B);
-    kern<<<grid, Cfg::THREADS, smem, st>>>(m_rgb, m_sig, m_obj, p);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(m_rgb, m_sig, m_obj, m_sigd, p);
     *used = true;
     return mf_launch_status();
 }
 
 // tile 64x16, box 80x24, 4-stage ring, 2 pixels per thread: 153.6 KB of stages, 1 CTA / SM
 typedef TmaCfg<64, 16, 80, 24, 4, 2> CfgDefault;
+// experimental shapes, selected with MPIFLOW_TMA_CFG=1..3 (A/B measurements only)
+typedef TmaCfg<64, 8, 80, 16, 3, 2, 2> CfgHalf;     // 64x8 tiles, 2 CTAs / SM
+typedef TmaCfg<32, 16, 48, 24, 4, 2, 2> CfgNarrow;  // 32x16 tiles, 2 CTAs / SM
+typedef TmaCfg<64, 16, 80, 24, 3, 2> CfgShallow;    // 3-stage ring
+
+static int tma_cfg()
+{
+    static const int v = []() {
+        const char *e = getenv("MPIFLOW_TMA_CFG");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
 
 // MPIFLOW_RENDER_PATH=generic forces the plain global-load kernel (debugging / A-B measurements)
 static bool tma_enabled()
@@ -331,7 +347,12 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
 
     if (tma_enabled()) {
         bool used = false;
-        rc = launch_tma<CfgDefault>(p, st, &used);
+        switch (tma_cfg()) {
+            case 1: rc = launch_tma<CfgHalf>(p, st, &used); break;
+            case 2: rc = launch_tma<CfgNarrow>(p, st, &used); break;
+            case 3: rc = launch_tma<CfgShallow>(p, st, &used); break;
+            default: rc = launch_tma<CfgDefault>(p, st, &used); break;
+        }
         if (rc || used) return rc;
     }
     // generic path: tensors TMA cannot describe (W % 4 != 0, unaligned base, odd strides)

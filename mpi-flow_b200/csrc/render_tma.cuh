@@ -1,9 +1,10 @@
 // render_tma.cuh -- TMA-staged variant of the fused MPI renderer (sm_100a).
 //
-// CTA = one TW x TH tile of pixel indices of one batch entry.  For every plane s warp 0 (which also
+// CTA = one TW x TH tile of pixel indices of one batch entry.  For every plane s one warp (which also
 // renders) maps the tile corners through H_src_tgt(s) (same arithmetic as the pixels), derives the
-// source footprint, and issues three cp.async.bulk.tensor loads (rgb x3, sigma, object mask) of a
-// fixed BW x BH box around it into a STAGES-deep shared-memory ring guarded by full/empty mbarriers.
+// source footprint, and issues cp.async.bulk.tensor loads (rgb x3, sigma, object mask) of a
+// fixed BW x BH box around it into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
+// (the producer role rotates over the warps, plane by plane).
 // Consumer warps (PPT pixels per thread, same column, rows TH/PPT apart) take their four bilinear
 // taps per channel from shared memory with immediate offsets, so the plane loop has no 64-bit address
 // arithmetic and HBM/L2 latency is hidden by the ring instead of by occupancy.
@@ -11,6 +12,8 @@
 // global loads for that (tile, plane) only -- results are identical.
 #pragma once
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "homography.cuh"
 
@@ -80,38 +83,44 @@ __device__ __forceinline__ float fast_ex2(float v)
 }
 
 // ---- per-pixel state ---------------------------------------------------------------------------------
-// front-to-back accumulators of one pixel (mpi_rendering.py:79-96, :143-152) plus the plane that is
-// still waiting for its successor's geometry (its thickness is |xyz[s+1] - xyz[s]|, :68-71)
-struct PixelState {
+// front-to-back accumulators of one pixel (mpi_rendering.py:79-96, :143-152)
+struct PixelAcc {
     float acc, r, g, b, zsum, wsum, obj, cnt;  // target frame
-    float pr, pg, pb, psig, pm, pz;            // pending plane s-1
-    float pix, piy;                            // its clamped sample position
-    bool pclamped;
     float acc_s, fu, fv, best_w;               // source frame
 };
+// the plane that is still waiting for its successor's geometry (general path only): its thickness is
+// |xyz[s+1] - xyz[s]| evaluated at the two clamped sample positions (:68-71)
+struct Pending {
+    float r, g, b, sig, m, x, y, z;
+};
 
-template <int TW_, int TH_, int BW_, int BH_, int STAGES_, int PPT_>
+template <int TW_, int TH_, int BW_, int BH_, int STAGES_, int PPT_, int MINB_ = 1>
 struct TmaCfg {
+    static constexpr int MINB = MINB_;                    // CTAs per SM the register budget is sized for
     static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_, STAGES = STAGES_, PPT = PPT_;
     static constexpr int ROWS = TH / PPT;                 // rows per pass
     static constexpr int CONSUMER_WARPS = (TW / 32) * ROWS;
-    static constexpr int CONSUMERS = CONSUMER_WARPS * 32;
-    static constexpr int THREADS = CONSUMERS;             // warp 0 doubles as the TMA producer
+    static constexpr int THREADS = CONSUMER_WARPS * 32;   // warp 0 doubles as the TMA producer
     static constexpr int CH_FLOATS = BW * BH;             // one channel of one stage
-    static constexpr int STAGE_FLOATS = 5 * CH_FLOATS;    // r,g,b,sigma,obj
+    static constexpr int DIRECT_FLOATS = TW * TH;         // un-warped sigma of the tile itself
+    static constexpr int STAGE_FLOATS = 5 * CH_FLOATS + DIRECT_FLOATS;  // r,g,b,sigma,obj boxes + direct sigma
     static constexpr size_t STAGE_BYTES = (size_t)STAGE_FLOATS * sizeof(float);
     static_assert(TW % 32 == 0 && TH % PPT == 0 && BW % 4 == 0, "tile shape");
-    static_assert((CH_FLOATS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert((CH_FLOATS * 4) % 128 == 0 && (DIRECT_FLOATS * 4) % 128 == 0,
+                  "TMA destinations must stay 128-byte aligned");
     static size_t smem_bytes(int S)
     {
-        return 128 /*alignment slack*/ + STAGES * STAGE_BYTES + (size_t)S * sizeof(PlaneConst) + 2 * STAGES * 8 + STAGES * 16;
+        return STAGES * STAGE_BYTES + (size_t)S * sizeof(PlaneConst) + 2 * STAGES * 8 + STAGES * 16;
     }
 };
 
-template <class Cfg, bool HAS_OBJ>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+constexpr float MF_LOG2E = 1.4426950408889634f;
+
+template <class Cfg, bool HAS_OBJ, bool HARD>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __grid_constant__ CUtensorMap map_sig,
-                        const __grid_constant__ CUtensorMap map_obj, const RenderParams p)
+                        const __grid_constant__ CUtensorMap map_obj, const __grid_constant__ CUtensorMap map_sigd,
+                        const RenderParams p)
 {
     constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH, STAGES = Cfg::STAGES, PPT = Cfg::PPT;
     constexpr int CH = Cfg::CH_FLOATS;
@@ -168,45 +177,47 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
             ok &= __shfl_xor_sync(0xffffffffu, ok, o);
         }
         if (lane == 0) {
-            // 0.02 px of slack covers fp32 rounding of interior pixels relative to the corners
+            // 0.02 px of slack covers fp32 rounding of interior pixels relative to the corners;
             // TMA needs a 16-byte aligned box start in the innermost dimension: round x down to 4 texels
             const int bx = ((int)floorf(mnx - 0.02f)) & ~3, by = (int)floorf(mny - 0.02f);
             const int ex = (int)floorf(mxx + 0.02f) + 1, ey = (int)floorf(mxy + 0.02f) + 1;  // last tap col/row
             const bool fits = ok && (ex - bx + 1 <= BW) && (ey - by + 1 <= BH);
             meta[st] = make_int4(bx, by, fits ? 1 : 0, 0);
+            float *dst = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
+            const uint32_t box_bytes = fits ? (HAS_OBJ ? 5 : 4) * CH * (uint32_t)sizeof(float) : 0u;
+            mbar_arrive_expect_tx(&full[st], box_bytes + Cfg::DIRECT_FLOATS * (uint32_t)sizeof(float));
+            // the tile's own (un-warped) sigma for the source-frame weights, mpi_rendering.py:104-120
+            tma_load_4d(dst + 5 * CH, &map_sigd, &full[st], tx0, ty0, sl, b);
             if (fits) {
-                float *dst = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
-                mbar_arrive_expect_tx(&full[st], (HAS_OBJ ? 5 : 4) * CH * (uint32_t)sizeof(float));
                 tma_load_5d(dst, &map_rgb, &full[st], bx, by, 0, sl, b);
                 tma_load_4d(dst + 3 * CH, &map_sig, &full[st], bx, by, sl, b);
                 if (HAS_OBJ) tma_load_4d(dst + 4 * CH, &map_obj, &full[st], bx, by, p.obj_ss ? sl : 0, b);
-            } else {
-                mbar_arrive(&full[st]);
             }
         }
         __syncwarp();
     };
-    if (warp == 0)
-        for (int sl = 0; sl < STAGES - 1 && sl < S; sl++) produce(sl);
+    for (int sl = 0; sl < STAGES - 1 && sl < S; sl++)
+        if (warp == sl % Cfg::CONSUMER_WARPS) produce(sl);
 
-    const int xi = min(tx0 + (warp % (TW / 32)) * 32 + lane, W - 1);  // clamped: out-of-image threads
-    const int row0 = warp / (TW / 32);                                // recompute a border pixel
+    // ---- per-thread pixels: same column, rows ROWS apart (out-of-image threads recompute a border pixel) ----
+    const int xi = min(tx0 + (warp % (TW / 32)) * 32 + lane, W - 1);
+    const int row0 = warp / (TW / 32);
     const float xf = (float)xi;
     const BatchConst &bc = p.bc[b];
     const size_t HW = (size_t)H * W;
     const float *rgb_b = p.rgb + (size_t)b * p.rgb_sb;
     const float *sig_b = p.sigma + (size_t)b * p.sig_sb;
     const float *obj_b = HAS_OBJ ? p.obj + (size_t)b * p.obj_sb : nullptr;
-    const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
 
-    int yi[PPT];
     float yf[PPT], vnorm[PPT], tdist[PPT], invb[PPT];
-    PixelState ps[PPT];
-    float sig_next[PPT];
+    int yrow[PPT];  // row inside the tile
+    PixelAcc ps[PPT];
+    bool slow = false;
 #pragma unroll
     for (int j = 0; j < PPT; j++) {
-        yi[j] = min(ty0 + row0 + j * Cfg::ROWS, H - 1);
-        yf[j] = (float)yi[j];
+        const int yi = min(ty0 + row0 + j * Cfg::ROWS, H - 1);
+        yf[j] = (float)yi;
+        yrow[j] = yi - ty0;
         // source-frame ray |Kinv (x,y,1)|: spacing of planes s, s+1 along it = vnorm * (d[s+1]-d[s])
         const float v0 = mf_dot3(bc.kinv[0], bc.kinv[1], bc.kinv[2], xf, yf[j]);
         const float v1 = mf_dot3(bc.kinv[3], bc.kinv[4], bc.kinv[5], xf, yf[j]);
@@ -220,155 +231,171 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
         const float bq = fmaf(bc.rt2[2], r2, fmaf(bc.rt2[1], r1, bc.rt2[0] * r0));
         invb[j] = __frcp_rn(bq);
         tdist[j] = sqrtf(fmaf(r2, r2, fmaf(r1, r1, r0 * r0))) * fabsf(invb[j]);
-        PixelState &q = ps[j];
+        // The sample positions of all planes lie on one (epipolar) segment between those of the first
+        // and the last plane, so if neither end is clamped by the border no plane is, and the plane
+        // geometry along the pixel's own ray (above) is what the reference's warped xyz amounts to.
+        const SrcPos e0 = tgt_to_src(spc[0].hst, xf, yf[j], Wf, Hf, rW, rH);
+        const SrcPos e1 = tgt_to_src(spc[S - 1].hst, xf, yf[j], Wf, Hf, rW, rH);
+        const bool inside = e0.sx >= 0.f && e0.sx <= Wf - 1.f && e0.sy >= 0.f && e0.sy <= Hf - 1.f &&
+                            e1.sx >= 0.f && e1.sx <= Wf - 1.f && e1.sy >= 0.f && e1.sy <= Hf - 1.f;
+        slow = slow || !inside || !(bq > 1e-6f) || !(tdist[j] < 1e30f);
+        PixelAcc &q = ps[j];
         q.acc = 1.f; q.r = q.g = q.b = q.zsum = q.wsum = q.obj = q.cnt = 0.f;
-        q.pr = q.pg = q.pb = q.psig = q.pm = q.pz = q.pix = q.piy = 0.f;
-        q.pclamped = false;
         q.acc_s = 1.f; q.fu = q.fv = 0.f; q.best_w = -1.f;
-        sig_next[j] = __ldg(sig_b + (size_t)yi[j] * W + xi);
     }
+    slow = __any_sync(0xffffffffu, slow);  // warp-uniform choice of the plane loop
 
-    // composite plane s-1 once plane s's geometry is known
-    auto composite = [&](PixelState &q, float dist) {
-        const float T = fast_ex2(-q.psig * dist);  // dist carries log2(e)
-        const float w = q.acc * (1.f - T);
-        q.acc *= (T + 1e-6f);
-        q.wsum += w;
-        q.r = fmaf(w, q.pr, q.r);
-        q.g = fmaf(w, q.pg, q.g);
-        q.b = fmaf(w, q.pb, q.b);
-        q.zsum = fmaf(w, q.pz, q.zsum);
-        if (HAS_OBJ) q.obj = fmaf(w, q.pm, q.obj);
-    };
-    constexpr float LOG2E = 1.4426950408889634f;
-
-    for (int s = 0; s < S; s++) {
-        const int st = s % STAGES;
-        if (warp == 0 && s + STAGES - 1 < S) {
-            // the stage plane s-1 used is free once every warp has arrived on its empty barrier
-            if (s >= 1) mbar_wait(&empty[(s - 1) % STAGES], ((s - 1) / STAGES) & 1);
-            produce(s + STAGES - 1);
-        }
-        const PlaneConst &c = spc[s];
-        const float *sm = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
-        mbar_wait(&full[st], (s / STAGES) & 1);
-        // un-warped sigma of the NEXT plane for the source-frame weights: issued now (asm volatile keeps
-        // it here), consumed one iteration later, so its L2 latency hides behind this plane's work
-        float sig_pref[PPT];
-        {
-            const float *sn = sig_b + (size_t)min(s + 1, S - 1) * p.sig_ss;
+    // `GENERAL` keeps one plane pending and measures thickness between clamped sample positions
+    // (border warps); otherwise thickness and depth come from the pixel's ray and nothing is pending.
+    auto plane_loop = [&](auto general_tag) {
+        constexpr bool GENERAL = decltype(general_tag)::value;
+        Pending pd[GENERAL ? PPT : 1];
+        if (GENERAL) {
 #pragma unroll
-            for (int j = 0; j < PPT; j++)
-                asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(sig_pref[j]) : "l"(sn + (size_t)yi[j] * W + xi));
+            for (int j = 0; j < PPT; j++) pd[j] = Pending{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         }
-        const int4 mt = meta[st];
-        const bool last = (s + 1 == S);
-        const float zc = c.depth + bc.a;  // numerator of Z_s
-        // shared by the PPT pixels of this thread (same column): first product of each FMA chain
-        const float hx0 = __fmul_rn(c.hst[0], xf), hx3 = __fmul_rn(c.hst[3], xf), hx6 = __fmul_rn(c.hst[6], xf);
-        const float gx0 = __fmul_rn(c.hts[0], xf), gx3 = __fmul_rn(c.hts[3], xf), gx6 = __fmul_rn(c.hts[6], xf);
-        const float *sig_s = sig_b + (size_t)s * p.sig_ss;
-#pragma unroll
-        for (int j = 0; j < PPT; j++) {
-            PixelState &q = ps[j];
-            // ---------------- target frame: position ----------------
-            const float X = __fadd_rn(__fmaf_rn(c.hst[1], yf[j], hx0), c.hst[2]);
-            const float Y = __fadd_rn(__fmaf_rn(c.hst[4], yf[j], hx3), c.hst[5]);
-            const float Z = __fadd_rn(__fmaf_rn(c.hst[7], yf[j], hx6), c.hst[8]);
-            float sx, sy;
-            mf_div2(X, Y, Z, sx, sy);
-            const bool valid = (sx < Wf) && (sx > -1.f) && (sy < Hf) && (sy > -1.f);
-            q.cnt += valid ? 1.f : 0.f;
-            const float gx = __fadd_rn(__fmul_rn(__fadd_rn(sx, 0.5f), rW), -1.f);
-            const float gy = __fadd_rn(__fmul_rn(__fadd_rn(sy, 0.5f), rH), -1.f);
-            const float ixu = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), Wf, -1.f), 0.5f);
-            const float iyu = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), Hf, -1.f), 0.5f);
-            const float ix = fminf(Wf - 1.f, fmaxf(ixu, 0.f));
-            const float iy = fminf(Hf - 1.f, fmaxf(iyu, 0.f));
-            const bool clamped = (ix != ixu) || (iy != iyu);
-            const float x0f = floorf(ix), y0f = floorf(iy);
-            const float wx1 = __fsub_rn(__fadd_rn(x0f, 1.f), ix), wx0 = __fsub_rn(ix, x0f);
-            const float wy1 = __fsub_rn(__fadd_rn(y0f, 1.f), iy), wy0 = __fsub_rn(iy, y0f);
-            const float nw = __fmul_rn(wx1, wy1), ne = __fmul_rn(wx0, wy1);
-            const float sw = __fmul_rn(wx1, wy0), se = __fmul_rn(wx0, wy0);
-            const int x0 = (int)x0f, y0 = (int)y0f;
-            float cr, cg, cb, sg, m = 0.f;
-            if (mt.z) {  // warp-uniform: the plane's footprint is in shared memory
-                const float *t = sm + (y0 - mt.y) * BW + (x0 - mt.x);
-                auto tap = [&](const float *u) {
-                    float a = __fmul_rn(u[0], nw);
-                    a = __fmaf_rn(u[1], ne, a);
-                    a = __fmaf_rn(u[BW], sw, a);
-                    return __fmaf_rn(u[BW + 1], se, a);
-                };
-                cr = tap(t); cg = tap(t + CH); cb = tap(t + 2 * CH); sg = tap(t + 3 * CH);
-                if (HAS_OBJ) m = tap(t + 4 * CH);
-            } else {     // same taps straight from global memory
-                const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-                const int o00 = y0 * W + x0, o01 = y0 * W + x1, o10 = y1 * W + x0, o11 = y1 * W + x1;
-                auto tap = [&](const float *img) {
-                    float a = __fmul_rn(__ldg(img + o00), nw);
-                    a = __fmaf_rn(__ldg(img + o01), ne, a);
-                    a = __fmaf_rn(__ldg(img + o10), sw, a);
-                    return __fmaf_rn(__ldg(img + o11), se, a);
-                };
+        auto composite = [&](PixelAcc &q, float sg, float dist_l2e, float cr, float cg, float cb, float z, float m) {
+            const float T = fast_ex2(-sg * dist_l2e);  // exp(-sigma*dist) (:79)
+            const float w = q.acc * (1.f - T);         // :80, :89
+            q.acc *= (T + 1e-6f);                      // :84
+            q.wsum += w;
+            q.r = fmaf(w, cr, q.r);
+            q.g = fmaf(w, cg, q.g);
+            q.b = fmaf(w, cb, q.b);
+            q.zsum = fmaf(w, z, q.zsum);
+            if (HAS_OBJ) q.obj = fmaf(w, m, q.obj);
+        };
+        for (int s = 0; s < S; s++) {
+            const int st = s % STAGES;
+            // The producer role rotates over the warps (plane sl is fetched by warp sl % #warps): a fixed
+            // producer warp would be permanently behind by its extra work, and since nobody can run more
+            // than STAGES-1 planes ahead of the producer the whole CTA would run at that warp's
+            // single-warp speed.
+            if (s + STAGES - 1 < S && warp == (s + STAGES - 1) % Cfg::CONSUMER_WARPS) {
+                // the stage plane s-1 used is free once every warp has arrived on its empty barrier
+                if (s >= 1) mbar_wait(&empty[(s - 1) % STAGES], ((s - 1) / STAGES) & 1);
+                produce(s + STAGES - 1);
+            }
+            const PlaneConst &c = spc[s];
+            const bool last = (s + 1 == S);
+            mbar_wait(&full[st], (s / STAGES) & 1);
+            const int4 mt = meta[st];
+            // tap address = tile_base + y0*BW + x0 (box origin folded in once per plane)
+            const float *tile_base = stage_buf + (size_t)st * Cfg::STAGE_FLOATS - (mt.y * BW + mt.x);
+            // this thread's un-warped sigma values of plane s (clamped column/rows stay inside the tile)
+            const float *sig_direct = stage_buf + (size_t)st * Cfg::STAGE_FLOATS + 5 * CH + (xi - tx0);
+            const float zc = c.depth + bc.a;  // numerator of the plane's depth along the pixel ray
+            const float dl2e = c.ddepth_l2e;
+            // shared by this thread's pixels (same column): first product of each FMA chain
+            const float hx0 = __fmul_rn(c.hst[0], xf), hx3 = __fmul_rn(c.hst[3], xf), hx6 = __fmul_rn(c.hst[6], xf);
+            const float gx0 = __fmul_rn(c.hts[0], xf), gx3 = __fmul_rn(c.hts[3], xf), gx6 = __fmul_rn(c.hts[6], xf);
+            // One straight-line block for all of this thread's pixels (the only branch, "is the footprint
+            // in shared memory", is taken outside), so the scheduler can interleave their dependency chains.
+            auto body = [&](auto fits_tag) {
+                constexpr bool FITS = decltype(fits_tag)::value;
                 const float *rgb_s = rgb_b + (size_t)s * p.rgb_ss;
-                cr = tap(rgb_s); cg = tap(rgb_s + p.rgb_sc); cb = tap(rgb_s + 2 * p.rgb_sc);
-                sg = tap(sig_s);
-                if (HAS_OBJ) m = tap(obj_b + (size_t)s * p.obj_ss);
-            }
-            // ---------------- target frame: geometry + composite of plane s-1 ----------------
-            float Zt;
-            if (!(clamped || q.pclamped)) {
-                Zt = zc * invb[j];
-                if (s > 0) composite(q, tdist[j] * spc[s - 1].ddepth_l2e);
-            } else {
-                // a clamped sample leaves the pixel's ray: evaluate xyz_tgt at the clamped positions
-                const float Xc = fmaf(c.P[0], ix, fmaf(c.P[1], iy, c.P[2]));
-                const float Yc = fmaf(c.P[3], ix, fmaf(c.P[4], iy, c.P[5]));
-                Zt = fmaf(c.P[6], ix, fmaf(c.P[7], iy, c.P[8]));
-                if (s > 0) {
-                    const PlaneConst &cp = spc[s - 1];
-                    const float Xp = fmaf(cp.P[0], q.pix, fmaf(cp.P[1], q.piy, cp.P[2]));
-                    const float Yp = fmaf(cp.P[3], q.pix, fmaf(cp.P[4], q.piy, cp.P[5]));
-                    const float Zp = fmaf(cp.P[6], q.pix, fmaf(cp.P[7], q.piy, cp.P[8]));
-                    const float dx = Xc - Xp, dy = Yc - Yp, dz = Zt - Zp;
-                    q.pz = Zp;
-                    composite(q, fast_sqrt(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * LOG2E);
-                }
-            }
-            q.pr = cr; q.pg = cg; q.pb = cb; q.pm = m; q.pz = Zt;
-            q.psig = (Zt >= 0.f) ? sg : 0.f;  // :334-338
-            q.pix = ix; q.piy = iy; q.pclamped = clamped;
-
-            // ---------------- source frame ----------------
-            const float U = __fadd_rn(__fmaf_rn(c.hts[1], yf[j], gx0), c.hts[2]);
-            const float V = __fadd_rn(__fmaf_rn(c.hts[4], yf[j], gx3), c.hts[5]);
-            const float Q = __fadd_rn(__fmaf_rn(c.hts[7], yf[j], gx6), c.hts[8]);
-            float tu, tv;
-            mf_div2(U, V, Q, tu, tv);
-            const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf[j]);  // :212-218
-            const float sgs = sig_next[j];
-            const float Ts = fast_ex2(-sgs * (last ? 1e3f * LOG2E : vnorm[j] * c.ddepth_l2e));
-            const float ws = q.acc_s * (1.f - Ts);
-            q.acc_s *= (Ts + 1e-6f);
-            if (hard) {
-                if (ws > q.best_w) { q.best_w = ws; q.fu = du; q.fv = dv; }
-            } else {
-                q.fu = fmaf(ws, du, q.fu);
-                q.fv = fmaf(ws, dv, q.fv);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+                const float *sig_s = sig_b + (size_t)s * p.sig_ss;
+                const float *obj_s = HAS_OBJ ? obj_b + (size_t)s * p.obj_ss : nullptr;
 #pragma unroll
-        for (int j = 0; j < PPT; j++) sig_next[j] = sig_pref[j];
-    }
+                for (int j = 0; j < PPT; j++) {
+                    PixelAcc &q = ps[j];
+                    // ------------- target frame: sample position (homography_sampler.py:131-154) -------------
+                    const float X = __fadd_rn(__fmaf_rn(c.hst[1], yf[j], hx0), c.hst[2]);
+                    const float Y = __fadd_rn(__fmaf_rn(c.hst[4], yf[j], hx3), c.hst[5]);
+                    const float Z = __fadd_rn(__fmaf_rn(c.hst[7], yf[j], hx6), c.hst[8]);
+                    float sx, sy;
+                    mf_div2(X, Y, Z, sx, sy);
+                    bool valid = sx > -1.f;
+                    valid = valid && (sx < Wf);
+                    valid = valid && (sy > -1.f);
+                    valid = valid && (sy < Hf);
+                    q.cnt += valid ? 1.f : 0.f;  // :143-147, mpi_rendering.py:347
+                    const float gx = __fadd_rn(__fmul_rn(__fadd_rn(sx, 0.5f), rW), -1.f);
+                    const float gy = __fadd_rn(__fmul_rn(__fadd_rn(sy, 0.5f), rH), -1.f);
+                    const float ixu = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), Wf, -1.f), 0.5f);
+                    const float iyu = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.f), Hf, -1.f), 0.5f);
+                    const float ix = fminf(Wf - 1.f, fmaxf(ixu, 0.f));
+                    const float iy = fminf(Hf - 1.f, fmaxf(iyu, 0.f));
+                    // bilinear weights; (x0+1)-ix and 1-(ix-x0) are the same real number, ix-x0 is exact
+                    const float x0f = floorf(ix), y0f = floorf(iy);
+                    const float wx0 = __fsub_rn(ix, x0f), wy0 = __fsub_rn(iy, y0f);
+                    const float wx1 = __fsub_rn(1.f, wx0), wy1 = __fsub_rn(1.f, wy0);
+                    const float nw = __fmul_rn(wx1, wy1), ne = __fmul_rn(wx0, wy1);
+                    const float sw = __fmul_rn(wx1, wy0), se = __fmul_rn(wx0, wy0);
+                    const int x0 = (int)x0f, y0 = (int)y0f;
+                    float cr, cg, cb, sg, m = 0.f;
+                    if (FITS) {  // the plane's footprint is in shared memory
+                        const float *t = tile_base + (y0 * BW + x0);
+                        auto tap = [&](const float *u) {
+                            float a = __fmul_rn(u[0], nw);
+                            a = __fmaf_rn(u[1], ne, a);
+                            a = __fmaf_rn(u[BW], sw, a);
+                            return __fmaf_rn(u[BW + 1], se, a);
+                        };
+                        cr = tap(t); cg = tap(t + CH); cb = tap(t + 2 * CH); sg = tap(t + 3 * CH);
+                        if (HAS_OBJ) m = tap(t + 4 * CH);
+                    } else {     // same taps straight from global memory
+                        const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+                        const int o00 = y0 * W + x0, o01 = y0 * W + x1, o10 = y1 * W + x0, o11 = y1 * W + x1;
+                        auto tap = [&](const float *img) {
+                            float a = __fmul_rn(__ldg(img + o00), nw);
+                            a = __fmaf_rn(__ldg(img + o01), ne, a);
+                            a = __fmaf_rn(__ldg(img + o10), sw, a);
+                            return __fmaf_rn(__ldg(img + o11), se, a);
+                        };
+                        cr = tap(rgb_s); cg = tap(rgb_s + p.rgb_sc); cb = tap(rgb_s + 2 * p.rgb_sc);
+                        sg = tap(sig_s);
+                        if (HAS_OBJ) m = tap(obj_s);
+                    }
+                    // ------------- target frame: plane geometry + compositing -------------
+                    if (!GENERAL) {
+                        const float Zt = zc * invb[j];
+                        sg = (Zt >= 0.f) ? sg : 0.f;  // mpi_rendering.py:334-338
+                        composite(q, sg, last ? 1e3f * MF_LOG2E : tdist[j] * dl2e, cr, cg, cb, Zt, m);  // :73-78
+                    } else {
+                        // xyz_tgt of the plane at the (possibly clamped) sample position
+                        const float Xc = fmaf(c.P[0], ix, fmaf(c.P[1], iy, c.P[2]));
+                        const float Yc = fmaf(c.P[3], ix, fmaf(c.P[4], iy, c.P[5]));
+                        const float Zt = fmaf(c.P[6], ix, fmaf(c.P[7], iy, c.P[8]));
+                        Pending &d = pd[j];
+                        if (s > 0) {
+                            const float dx = Xc - d.x, dy = Yc - d.y, dz = Zt - d.z;
+                            composite(q, d.sig, fast_sqrt(fmaf(dz, dz, fmaf(dy, dy, dx * dx))) * MF_LOG2E, d.r, d.g, d.b, d.z, d.m);
+                        }
+                        d = Pending{cr, cg, cb, (Zt >= 0.f) ? sg : 0.f, m, Xc, Yc, Zt};
+                        if (last) composite(q, d.sig, 1e3f * MF_LOG2E, d.r, d.g, d.b, d.z, d.m);  // :73-78
+                    }
+                    // ------------- source frame (homography_sampler.py:207-218, mpi_rendering.py:102-133) ------
+                    const float U = __fadd_rn(__fmaf_rn(c.hts[1], yf[j], gx0), c.hts[2]);
+                    const float V = __fadd_rn(__fmaf_rn(c.hts[4], yf[j], gx3), c.hts[5]);
+                    const float Q = __fadd_rn(__fmaf_rn(c.hts[7], yf[j], gx6), c.hts[8]);
+                    float tu, tv;
+                    mf_div2(U, V, Q, tu, tv);
+                    const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf[j]);
+                    const float sgs = sig_direct[(yrow[j]) * TW];
+                    const float Ts = fast_ex2(-sgs * (last ? 1e3f * MF_LOG2E : vnorm[j] * dl2e));
+                    const float ws = q.acc_s * (1.f - Ts);
+                    q.acc_s *= (Ts + 1e-6f);
+                    if (HARD) {  // one-hot of the first arg-max weight (:126-130)
+                        if (ws > q.best_w) { q.best_w = ws; q.fu = du; q.fv = dv; }
+                    } else {
+                        q.fu = fmaf(ws, du, q.fu);
+                        q.fv = fmaf(ws, dv, q.fv);
+                    }
+                }
+            };
+            if (mt.z) body(std::true_type{});
+            else body(std::false_type{});
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+    };
+    if (slow) plane_loop(std::true_type{});
+    else plane_loop(std::false_type{});
 
 #pragma unroll
     for (int j = 0; j < PPT; j++) {
-        PixelState &q = ps[j];
-        composite(q, 1e3f * LOG2E);  // last plane: thickness 1e3 (:73-78)
+        const PixelAcc &q = ps[j];
         const int x = tx0 + (warp % (TW / 32)) * 32 + lane, y = ty0 + row0 + j * Cfg::ROWS;
         if (x >= W || y >= H) continue;
         const size_t o = (size_t)y * W + x;
