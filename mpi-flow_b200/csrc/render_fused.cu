@@ -281,10 +281,11 @@ static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
     return mf_launch_status();
 }
 
-// tile 64x16, box 80x24, 4-stage ring, 2 pixels per thread: 153.6 KB of stages, 1 CTA / SM
-typedef TmaCfg<64, 16, 80, 24, 4, 2> CfgDefault;
+// tile 64x8, box 80x16, 3-stage ring, 2 pixels per thread, 8 warps, 2 CTAs / SM (independent rings
+// fill each other's barrier waits): 83 KB of stages + 8 KB of plane constants per CTA
+typedef TmaCfg<64, 8, 80, 16, 3, 2, 2> CfgDefault;
 // experimental shapes, selected with MPIFLOW_TMA_CFG=1..3 (A/B measurements only)
-typedef TmaCfg<64, 8, 80, 16, 3, 2, 2> CfgHalf;     // 64x8 tiles, 2 CTAs / SM
+typedef TmaCfg<64, 16, 80, 24, 4, 2> CfgFull;        // 64x16 tiles, 16 warps, 1 CTA / SM
 typedef TmaCfg<32, 16, 48, 24, 4, 2, 2> CfgNarrow;  // 32x16 tiles, 2 CTAs / SM
 typedef TmaCfg<64, 16, 80, 24, 3, 2> CfgShallow;    // 3-stage ring
 
@@ -348,7 +349,7 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     if (tma_enabled()) {
         bool used = false;
         switch (tma_cfg()) {
-            case 1: rc = launch_tma<CfgHalf>(p, st, &used); break;
+            case 1: rc = launch_tma<CfgFull>(p, st, &used); break;
             case 2: rc = launch_tma<CfgNarrow>(p, st, &used); break;
             case 3: rc = launch_tma<CfgShallow>(p, st, &used); break;
             default: rc = launch_tma<CfgDefault>(p, st, &used); break;

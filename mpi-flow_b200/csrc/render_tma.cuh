@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
@@ -68,6 +68,15 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// shared-memory load at a 32-bit shared-window address + compile-time byte offset (keeps the tap
+// addressing to one register and immediates; no generic->shared conversion inside the plane loop)
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
 }
 __device__ __forceinline__ float fast_sqrt(float v)
 {
@@ -110,7 +119,7 @@ struct TmaCfg {
                   "TMA destinations must stay 128-byte aligned");
     static size_t smem_bytes(int S)
     {
-        return STAGES * STAGE_BYTES + (size_t)S * sizeof(PlaneConst) + 2 * STAGES * 8 + STAGES * 16;
+        return STAGES * STAGE_BYTES + (size_t)S * sizeof(PlaneConst) + 2 * STAGES * 8 + 2 * STAGES * 16;
     }
 };
 
@@ -130,9 +139,12 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
     float *stage_buf = reinterpret_cast<float *>(smem_raw);
     PlaneConst *spc = reinterpret_cast<PlaneConst *>(smem_raw + STAGES * Cfg::STAGE_BYTES);
     const int S = p.S, H = p.H, W = p.W;
-    uint64_t *full = reinterpret_cast<uint64_t *>(spc + S);
-    uint64_t *empty = full + STAGES;
-    int4 *meta = reinterpret_cast<int4 *>(empty + STAGES);  // {bx, by, fits, -}
+    // the plan of plane sl is written when its stage is free, i.e. after everybody has read the plan of
+    // plane sl-STAGES; planes in between are still live: 2*STAGES slots keep them apart
+    constexpr int PLAN_SLOTS = 2 * STAGES;
+    int4 *meta = reinterpret_cast<int4 *>(spc + S);                              // plans {bx, by, fits, -}
+    uint64_t *full = reinterpret_cast<uint64_t *>(meta + PLAN_SLOTS);            // "stage filled" mbarriers
+    uint64_t *empty = full + STAGES;                                             // "stage consumed" mbarriers
 
     const int b = blockIdx.z;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
@@ -157,12 +169,11 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
     const float Wf = (float)W, Hf = (float)H;
     const float rW = __frcp_rn(Wf * 0.5f), rH = __frcp_rn(Hf * 0.5f);
 
-    // ---- producer role (warp 0): footprint of plane sl for this tile -> TMA into stage sl % STAGES ----
-    // lanes 0..3 own the four (clamped-to-image) corners of the tile
+    // ---- producer role: plan(sl) derives the footprint of plane sl for this tile (lanes 0..3 own the four
+    // clamped-to-image tile corners), issue(sl) fires the TMA loads into stage sl % STAGES ----
     const int cx = min(tx0 + ((lane & 1) ? TW - 1 : 0), W - 1);
     const int cy = min(ty0 + ((lane & 2) ? TH - 1 : 0), H - 1);
-    auto produce = [&](int sl) {
-        const int st = sl % STAGES;
+    auto plan = [&](int sl) {
         const PlaneConst &c = spc[sl];
         const SrcPos sp = tgt_to_src(c.hst, (float)cx, (float)cy, Wf, Hf, rW, rH);
         const float Zc = mf_dot3(c.hst[6], c.hst[7], c.hst[8], (float)cx, (float)cy);
@@ -182,22 +193,29 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
             const int bx = ((int)floorf(mnx - 0.02f)) & ~3, by = (int)floorf(mny - 0.02f);
             const int ex = (int)floorf(mxx + 0.02f) + 1, ey = (int)floorf(mxy + 0.02f) + 1;  // last tap col/row
             const bool fits = ok && (ex - bx + 1 <= BW) && (ey - by + 1 <= BH);
-            meta[st] = make_int4(bx, by, fits ? 1 : 0, 0);
-            float *dst = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
-            const uint32_t box_bytes = fits ? (HAS_OBJ ? 5 : 4) * CH * (uint32_t)sizeof(float) : 0u;
-            mbar_arrive_expect_tx(&full[st], box_bytes + Cfg::DIRECT_FLOATS * (uint32_t)sizeof(float));
-            // the tile's own (un-warped) sigma for the source-frame weights, mpi_rendering.py:104-120
-            tma_load_4d(dst + 5 * CH, &map_sigd, &full[st], tx0, ty0, sl, b);
-            if (fits) {
-                tma_load_5d(dst, &map_rgb, &full[st], bx, by, 0, sl, b);
-                tma_load_4d(dst + 3 * CH, &map_sig, &full[st], bx, by, sl, b);
-                if (HAS_OBJ) tma_load_4d(dst + 4 * CH, &map_obj, &full[st], bx, by, p.obj_ss ? sl : 0, b);
-            }
+            meta[sl % PLAN_SLOTS] = make_int4(bx, by, fits ? 1 : 0, 0);
         }
         __syncwarp();
     };
+    auto issue = [&](int sl) {  // one thread
+        const int st = sl % STAGES;
+        const int4 mt = meta[sl % PLAN_SLOTS];
+        float *dst = stage_buf + (size_t)st * Cfg::STAGE_FLOATS;
+        const uint32_t box_bytes = mt.z ? (HAS_OBJ ? 5 : 4) * CH * (uint32_t)sizeof(float) : 0u;
+        mbar_arrive_expect_tx(&full[st], box_bytes + Cfg::DIRECT_FLOATS * (uint32_t)sizeof(float));
+        // the tile's own (un-warped) sigma for the source-frame weights, mpi_rendering.py:104-120
+        tma_load_4d(dst + 5 * CH, &map_sigd, &full[st], tx0, ty0, sl, b);
+        if (mt.z) {
+            tma_load_5d(dst, &map_rgb, &full[st], mt.x, mt.y, 0, sl, b);
+            tma_load_4d(dst + 3 * CH, &map_sig, &full[st], mt.x, mt.y, sl, b);
+            if (HAS_OBJ) tma_load_4d(dst + 4 * CH, &map_obj, &full[st], mt.x, mt.y, p.obj_ss ? sl : 0, b);
+        }
+    };
     for (int sl = 0; sl < STAGES - 1 && sl < S; sl++)
-        if (warp == sl % Cfg::CONSUMER_WARPS) produce(sl);
+        if (warp == sl % Cfg::CONSUMER_WARPS) {
+            plan(sl);
+            if (lane == 0) issue(sl);
+        }
 
     // ---- per-thread pixels: same column, rows ROWS apart (out-of-image threads recompute a border pixel) ----
     const int xi = min(tx0 + (warp % (TW / 32)) * 32 + lane, W - 1);
@@ -210,14 +228,16 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
     const float *obj_b = HAS_OBJ ? p.obj + (size_t)b * p.obj_sb : nullptr;
 
     float yf[PPT], vnorm[PPT], tdist[PPT], invb[PPT];
-    int yrow[PPT];  // row inside the tile
+    uint32_t sd_off[PPT];  // byte offset of the pixel's un-warped sigma inside a stage
+    const float bc_a = bc.a;
+    const uint32_t stage0_u32 = smem_u32(stage_buf);
     PixelAcc ps[PPT];
     bool slow = false;
 #pragma unroll
     for (int j = 0; j < PPT; j++) {
         const int yi = min(ty0 + row0 + j * Cfg::ROWS, H - 1);
         yf[j] = (float)yi;
-        yrow[j] = yi - ty0;
+        sd_off[j] = (uint32_t)(5 * CH + (yi - ty0) * TW + (xi - tx0)) * 4u;
         // source-frame ray |Kinv (x,y,1)|: spacing of planes s, s+1 along it = vnorm * (d[s+1]-d[s])
         const float v0 = mf_dot3(bc.kinv[0], bc.kinv[1], bc.kinv[2], xf, yf[j]);
         const float v1 = mf_dot3(bc.kinv[3], bc.kinv[4], bc.kinv[5], xf, yf[j]);
@@ -274,18 +294,21 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
             if (s + STAGES - 1 < S && warp == (s + STAGES - 1) % Cfg::CONSUMER_WARPS) {
                 // the stage plane s-1 used is free once every warp has arrived on its empty barrier
                 if (s >= 1) mbar_wait(&empty[(s - 1) % STAGES], ((s - 1) / STAGES) & 1);
-                produce(s + STAGES - 1);
+                plan(s + STAGES - 1);
+                if (lane == 0) issue(s + STAGES - 1);
             }
             const PlaneConst &c = spc[s];
             const bool last = (s + 1 == S);
             mbar_wait(&full[st], (s / STAGES) & 1);
-            const int4 mt = meta[st];
-            // tap address = tile_base + y0*BW + x0 (box origin folded in once per plane)
-            const float *tile_base = stage_buf + (size_t)st * Cfg::STAGE_FLOATS - (mt.y * BW + mt.x);
-            // this thread's un-warped sigma values of plane s (clamped column/rows stay inside the tile)
-            const float *sig_direct = stage_buf + (size_t)st * Cfg::STAGE_FLOATS + 5 * CH + (xi - tx0);
-            const float zc = c.depth + bc.a;  // numerator of the plane's depth along the pixel ray
-            const float dl2e = c.ddepth_l2e;
+            const int4 mt = meta[s % PLAN_SLOTS];
+            // 32-bit shared-window addresses: stage base, and the tile base with the box origin folded in
+            // (tap address = tile_u32 + 4*(y0*BW + x0) + immediates)
+            const uint32_t stage_u32 = stage0_u32 + (uint32_t)st * (uint32_t)Cfg::STAGE_BYTES;
+            const uint32_t tile_u32 = stage_u32 - (uint32_t)(mt.y * BW + mt.x) * 4u;
+            const float zc = c.depth + bc_a;  // numerator of the plane's depth along the pixel ray
+            // thickness of plane s along a ray of unit parameter: d[s+1]-d[s], or 1e3 for the last plane
+            // (mpi_rendering.py:73-78); both carry log2(e) for ex2
+            const float dmul = last ? 0.f : c.ddepth_l2e, dadd = last ? 1e3f * MF_LOG2E : 0.f;
             // shared by this thread's pixels (same column): first product of each FMA chain
             const float hx0 = __fmul_rn(c.hst[0], xf), hx3 = __fmul_rn(c.hst[3], xf), hx6 = __fmul_rn(c.hst[6], xf);
             const float gx0 = __fmul_rn(c.hts[0], xf), gx3 = __fmul_rn(c.hts[3], xf), gx6 = __fmul_rn(c.hts[6], xf);
@@ -293,9 +316,14 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
             // in shared memory", is taken outside), so the scheduler can interleave their dependency chains.
             auto body = [&](auto fits_tag) {
                 constexpr bool FITS = decltype(fits_tag)::value;
-                const float *rgb_s = rgb_b + (size_t)s * p.rgb_ss;
-                const float *sig_s = sig_b + (size_t)s * p.sig_ss;
-                const float *obj_s = HAS_OBJ ? obj_b + (size_t)s * p.obj_ss : nullptr;
+                const float *rgb_s = nullptr, *sig_s = nullptr, *obj_s = nullptr;
+                if (!FITS) {
+                    int so = s;
+                    asm volatile("" : "+r"(so));  // keep these out of the loop's induction variables
+                    rgb_s = rgb_b + (size_t)so * p.rgb_ss;
+                    sig_s = sig_b + (size_t)so * p.sig_ss;
+                    obj_s = HAS_OBJ ? obj_b + (size_t)so * p.obj_ss : nullptr;
+                }
 #pragma unroll
                 for (int j = 0; j < PPT; j++) {
                     PixelAcc &q = ps[j];
@@ -305,11 +333,7 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
                     const float Z = __fadd_rn(__fmaf_rn(c.hst[7], yf[j], hx6), c.hst[8]);
                     float sx, sy;
                     mf_div2(X, Y, Z, sx, sy);
-                    bool valid = sx > -1.f;
-                    valid = valid && (sx < Wf);
-                    valid = valid && (sy > -1.f);
-                    valid = valid && (sy < Hf);
-                    q.cnt += valid ? 1.f : 0.f;  // :143-147, mpi_rendering.py:347
+                    if ((sx > -1.f) && (sx < Wf) && (sy > -1.f) && (sy < Hf)) q.cnt += 1.f;  // :143-147, mpi_rendering.py:347
                     const float gx = __fadd_rn(__fmul_rn(__fadd_rn(sx, 0.5f), rW), -1.f);
                     const float gy = __fadd_rn(__fmul_rn(__fadd_rn(sy, 0.5f), rH), -1.f);
                     const float ixu = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.f), Wf, -1.f), 0.5f);
@@ -325,15 +349,14 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
                     const int x0 = (int)x0f, y0 = (int)y0f;
                     float cr, cg, cb, sg, m = 0.f;
                     if (FITS) {  // the plane's footprint is in shared memory
-                        const float *t = tile_base + (y0 * BW + x0);
-                        auto tap = [&](const float *u) {
-                            float a = __fmul_rn(u[0], nw);
-                            a = __fmaf_rn(u[1], ne, a);
-                            a = __fmaf_rn(u[BW], sw, a);
-                            return __fmaf_rn(u[BW + 1], se, a);
-                        };
-                        cr = tap(t); cg = tap(t + CH); cb = tap(t + 2 * CH); sg = tap(t + 3 * CH);
-                        if (HAS_OBJ) m = tap(t + 4 * CH);
+                        const uint32_t t = tile_u32 + (uint32_t)(y0 * BW + x0) * 4u;
+#define MF_TAP(C)                                                                   \
+    __fmaf_rn(lds_f32<((C) * CH + BW + 1) * 4>(t), se,                               \
+              __fmaf_rn(lds_f32<((C) * CH + BW) * 4>(t), sw,                         \
+                        __fmaf_rn(lds_f32<((C) * CH + 1) * 4>(t), ne, __fmul_rn(lds_f32<(C) * CH * 4>(t), nw))))
+                        cr = MF_TAP(0); cg = MF_TAP(1); cb = MF_TAP(2); sg = MF_TAP(3);
+                        if (HAS_OBJ) m = MF_TAP(4);
+#undef MF_TAP
                     } else {     // same taps straight from global memory
                         const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
                         const int o00 = y0 * W + x0, o01 = y0 * W + x1, o10 = y1 * W + x0, o11 = y1 * W + x1;
@@ -351,7 +374,7 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
                     if (!GENERAL) {
                         const float Zt = zc * invb[j];
                         sg = (Zt >= 0.f) ? sg : 0.f;  // mpi_rendering.py:334-338
-                        composite(q, sg, last ? 1e3f * MF_LOG2E : tdist[j] * dl2e, cr, cg, cb, Zt, m);  // :73-78
+                        composite(q, sg, fmaf(tdist[j], dmul, dadd), cr, cg, cb, Zt, m);
                     } else {
                         // xyz_tgt of the plane at the (possibly clamped) sample position
                         const float Xc = fmaf(c.P[0], ix, fmaf(c.P[1], iy, c.P[2]));
@@ -372,8 +395,8 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
                     float tu, tv;
                     mf_div2(U, V, Q, tu, tv);
                     const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf[j]);
-                    const float sgs = sig_direct[(yrow[j]) * TW];
-                    const float Ts = fast_ex2(-sgs * (last ? 1e3f * MF_LOG2E : vnorm[j] * dl2e));
+                    const float sgs = lds_f32<0>(stage_u32 + sd_off[j]);  // un-warped sigma of plane s
+                    const float Ts = fast_ex2(-sgs * fmaf(vnorm[j], dmul, dadd));
                     const float ws = q.acc_s * (1.f - Ts);
                     q.acc_s *= (Ts + 1e-6f);
                     if (HARD) {  // one-hot of the first arg-max weight (:126-130)
