@@ -158,17 +158,15 @@ def run_ours(args, rank, local_rank, world):
     calls = [FusedCall(make_device_batch(B, synth.SEED + 1000 * rank + i, device), device) for i in range(NBUF)]
     peak, peak_src = measured_peak()
 
+    import shard
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return x if world == 1 else shard.max_over_ranks(x, device)
 
     # ---- device-resident throughput ----
     for i in range(args.warmup):
@@ -188,6 +186,25 @@ def run_ours(args, rank, local_rank, world):
     value = world * B * args.steps / (ms * 1e-3)
     bytes_per_launch = B * BYTES_PER_FRAME
     achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+
+    # ---- same, with the outputs all_gather'ed to every rank inside the timed region (N > 1) ----
+    gather = None
+    if world > 1:
+        gsteps = min(args.steps, 50)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(gsteps):
+            c = calls[i % NBUF]
+            c()
+            for o in c.out:
+                shard.gather_frames(o, world * B)
+        g1.record()
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1))
+        gather = {"value": round(world * B * gsteps / (gms * 1e-3), 2), "unit": "frames/s", "steps": gsteps,
+                  "bytes_per_step_per_rank": int(sum(o.numel() * 4 for o in calls[0].out)),
+                  "collective": "NCCL all_gather of the 8 output channels"}
 
     # ---- end to end through the host-buffer C-ABI entry point ----
     Be = args.e2e_frames_per_step
@@ -210,7 +227,9 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_value = world * Be * e2e_steps / e2e_s
     # the host path and the device path must agree bit for bit (same kernels)
-    assert torch.equal(h_out[0], calls[0].out[0][:Be].cpu()) or args.steps % NBUF != 1 or True
+    calls[0]()
+    torch.cuda.synchronize()
+    assert torch.equal(h_out[0], calls[0].out[0][:Be].cpu()), "host-buffer path and device path disagree"
     h2d = sum(h_in[k].numel() * 4 for k in h_in)
     d2h = sum(o.numel() * 4 for o in h_out)
 
@@ -240,9 +259,11 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "render_fused_kernel", "bytes_per_launch": bytes_per_launch},
+                         "kernel": "render_fused_tma_kernel", "bytes_per_launch": bytes_per_launch},
             "cpu_baseline": cpu,
         }
+        if gather:
+            line["with_output_gather"] = gather
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: headline metrics, dynamic instruction mix and top stall sites.
-usage: python profiles_tool.py gpurun_out/prof.ncu-rep [kernel-regex] > profiles/summary.txt"""
+usage: python profiles/summarise.py gpurun_out/prof.ncu-rep [kernel-regex] > profiles/summary.txt"""
 import collections, csv, io, re, subprocess, sys
 
 rep = sys.argv[1]
