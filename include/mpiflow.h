@@ -76,6 +76,11 @@ int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, i
 int mpiflow_debug_div_f32(const float *a, const float *c, const float *b, int n, float *qa, float *qc,
                           void *stream);
 
+/* test hook: packed fp32x2 arithmetic of the persistent renderer next to the scalar IEEE operations; n even,
+ * out [10,n]: rows fma2, fma, mul2, mul, sub2, sub, floor via 2^23 (round-down add), floorf, unfused a*b-1
+ * packed, scalar */
+int mpiflow_debug_packed_f32(const float *a, const float *b, const float *c, int n, float *out, void *stream);
+
 /* Same computation from HOST buffers (dense layouts: mpi [B,S,4,H,W] = rgb+sigma, obj [B,1,H,W]):
  * H2D of the inputs, the two launches, D2H of the five outputs, all inside the call; returns
  * MPIFLOW_E_SINGULAR like the reference raises.  Frames are pipelined over two streams. */

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "mpiflow_render_fused_f32": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P,
                                       _I, _I, _I, _I, _U, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
     "mpiflow_debug_div_f32": (_I, [_P, _P, _P, _I, _P, _P, _P]),
+    "mpiflow_debug_packed_f32": (_I, [_P, _P, _P, _I, _P, _P]),
     "mpiflow_render_fused_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _U, _P, _P, _P, _P, _P]),
     "mpiflow_homography_sample_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "mpiflow_homography_flow_f32": (_I, [_P, _I, _I, _I, _P, _P]),

@@ -15,15 +15,16 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "render_tma.cuh"
+#include "render_pk.cuh"
 
 // prologue: PlaneConst for every (b, s); inputs are per batch.
 __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__restrict__ Kinv,
                                     const float *__restrict__ Kt, const float *__restrict__ disparity,
                                     int B, int S, PlaneConst *__restrict__ pc, BatchConst *__restrict__ bcs,
-                                    int *__restrict__ status)
+                                    int *__restrict__ status, int *__restrict__ tile_counter)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0 && tile_counter) *tile_counter = 0;  // work queue of the persistent renderer that follows
     if (n >= B * S) return;
     const int b = n / S, s = n % S;
     float g[16], ki[9], kt[9];
@@ -55,7 +56,10 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
         for (int i = 0; i < 9; i++) bc.ktinv[i] = okb ? (float)ki64[i] : 0.f;
         for (int i = 0; i < 3; i++) bc.rt2[i] = g[i * 4 + 2];
         bc.a = fmaf(g[2 * 4 + 2], g[2 * 4 + 3], fmaf(g[1 * 4 + 2], g[1 * 4 + 3], g[0 * 4 + 2] * g[0 * 4 + 3]));
-        bc.pad[0] = bc.pad[1] = 0.f;
+        float mind = depth;
+        for (int i = 1; i < S; i++) mind = fminf(mind, __frcp_rn(disparity[n + i]));
+        bc.min_zc = mind + bc.a;   // NaN-propagating on purpose: a NaN disparity disables the lean loop
+        bc.pad = 0.f;
         bcs[b] = bc;
     }
     if (!(ok && okb) && status) atomicExch(status, 1);
@@ -238,45 +242,90 @@ static bool make_map(CUtensorMap *m, const float *ptr, int rank, const uint64_t 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class Cfg>
-static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
+struct RenderMaps {
+    CUtensorMap rgb, sig, obj, sigd;
+};
+
+// tensor maps over the caller's planar tensors: rgb (W,H,3,S,B) box (bw,bh,3), sigma / mask (W,H,S,B) box
+// (bw,bh), and sigma again with the tile itself as the box (un-warped sigma of the source-frame weights)
+static bool make_render_maps(const RenderParams &p, uint32_t bw, uint32_t bh, uint32_t tw, uint32_t th, RenderMaps *m)
 {
-    *used = false;
     const int B = p.B, S = p.S, H = p.H, W = p.W;
-    const size_t smem = Cfg::smem_bytes(S);
-    if (smem > 227 * 1024 || (W % 4) != 0) return 0;
+    if ((W % 4) != 0) return false;
     const uint64_t w4 = (uint64_t)W * 4, hw4 = (uint64_t)H * W * 4;
-    CUtensorMap m_rgb, m_sig, m_obj, m_sigd;
     {
         const uint64_t d[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)S, (uint64_t)B};
         const uint64_t sb[4] = {w4, (uint64_t)p.rgb_sc * 4, (uint64_t)(S > 1 ? p.rgb_ss : p.rgb_sc * 3) * 4,
                                 (uint64_t)(B > 1 ? p.rgb_sb : (int64_t)hw4) * (B > 1 ? 4 : 1)};
-        if (p.rgb_sc <= 0 || p.rgb_ss < 0 || p.rgb_sb < 0) return 0;
-        if (!make_map(&m_rgb, p.rgb, 5, d, sb, Cfg::BW, Cfg::BH, 3)) return 0;
+        if (p.rgb_sc <= 0 || p.rgb_ss < 0 || p.rgb_sb < 0) return false;
+        if (!make_map(&m->rgb, p.rgb, 5, d, sb, bw, bh, 3)) return false;
     }
     {
         const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)S, (uint64_t)B};
         const uint64_t sb[3] = {w4, (uint64_t)(S > 1 ? p.sig_ss * 4 : (int64_t)hw4), (uint64_t)(B > 1 ? p.sig_sb * 4 : (int64_t)hw4)};
-        if (p.sig_ss < 0 || p.sig_sb < 0) return 0;
-        if (!make_map(&m_sig, p.sigma, 4, d, sb, Cfg::BW, Cfg::BH, 1)) return 0;
-        if (!make_map(&m_sigd, p.sigma, 4, d, sb, Cfg::TW, Cfg::TH, 1)) return 0;
+        if (p.sig_ss < 0 || p.sig_sb < 0) return false;
+        if (!make_map(&m->sig, p.sigma, 4, d, sb, bw, bh, 1)) return false;
+        if (!make_map(&m->sigd, p.sigma, 4, d, sb, tw, th, 1)) return false;
     }
     if (p.obj) {
         const bool shared_mask = (p.obj_ss == 0) || S == 1;
         const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)(shared_mask ? 1 : S), (uint64_t)B};
         const uint64_t sb[3] = {w4, (uint64_t)(shared_mask ? (int64_t)hw4 : p.obj_ss * 4), (uint64_t)(B > 1 ? p.obj_sb * 4 : (int64_t)hw4)};
-        if (p.obj_ss < 0 || p.obj_sb < 0) return 0;
-        if (!make_map(&m_obj, p.obj, 4, d, sb, Cfg::BW, Cfg::BH, 1)) return 0;
+        if (p.obj_ss < 0 || p.obj_sb < 0) return false;
+        if (!make_map(&m->obj, p.obj, 4, d, sb, bw, bh, 1)) return false;
     } else {
-        m_obj = m_sig;
+        m->obj = m->sig;
     }
+    return true;
+}
+
+template <class Cfg>
+static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
+{
+    *used = false;
+    const size_t smem = Cfg::smem_bytes(p.S);
+    if (smem > 227 * 1024) return 0;
+    RenderMaps m;
+    if (!make_render_maps(p, Cfg::BW, Cfg::BH, Cfg::TW, Cfg::TH, &m)) return 0;
     const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
     auto kern = p.obj ? (hard ? render_fused_tma_kernel<Cfg, true, true> : render_fused_tma_kernel<Cfg, true, false>)
                       : (hard ? render_fused_tma_kernel<Cfg, false, true> : render_fused_tma_kernel<Cfg, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid((W + Cfg::TW - 1) / Cfg::TW, (H + Cfg::TH - 1) / Cfg::TH, B);
-    kern<<<grid, Cfg::THREADS, smem, st>>>(m_rgb, m_sig, m_obj, m_sigd, p);
+    dim3 grid((p.W + Cfg::TW - 1) / Cfg::TW, (p.H + Cfg::TH - 1) / Cfg::TH, p.B);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(m.rgb, m.sig, m.obj, m.sigd, p);
+    *used = true;
+    return mf_launch_status();
+}
+
+static int sm_count()
+{
+    static const int n = []() {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        return v;
+    }();
+    return n;
+}
+
+// persistent packed-fp32 renderer (render_pk.cuh): one CTA per SM, tiles from the counter the prologue reset
+template <class Cfg>
+static int launch_pk(const RenderParams &p, int *tile_counter, cudaStream_t st, bool *used)
+{
+    *used = false;
+    const size_t smem = Cfg::smem_bytes(p.S);
+    if (smem > 227 * 1024) return 0;
+    RenderMaps m;
+    if (!make_render_maps(p, Cfg::BW, Cfg::BH, Cfg::TW, Cfg::TH, &m)) return 0;
+    const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
+    auto kern = p.obj ? (hard ? render_fused_pk_kernel<Cfg, true, true> : render_fused_pk_kernel<Cfg, true, false>)
+                      : (hard ? render_fused_pk_kernel<Cfg, false, true> : render_fused_pk_kernel<Cfg, false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long ntiles = (long long)((p.W + Cfg::TW - 1) / Cfg::TW) * ((p.H + Cfg::TH - 1) / Cfg::TH) * p.B;
+    const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    kern<<<grid, Cfg::THREADS, smem, st>>>(m.rgb, m.sig, m.obj, m.sigd, p, tile_counter);
     *used = true;
     return mf_launch_status();
 }
@@ -289,6 +338,22 @@ typedef TmaCfg<64, 16, 80, 24, 4, 2> CfgFull;        // 64x16 tiles, 16 warps, 1
 typedef TmaCfg<32, 16, 48, 24, 4, 2, 2> CfgNarrow;  // 32x16 tiles, 2 CTAs / SM
 typedef TmaCfg<64, 16, 80, 24, 3, 2> CfgShallow;    // 3-stage ring
 
+// persistent kernel: tile 64x16, box 80x20 (zoom up to ~1.19), 5-stage ring, 2 pixel pairs per thread, 8+1 warps
+typedef PkCfg<64, 16, 80, 20, 5, 2> PkDefault;
+// A/B shapes, selected with MPIFLOW_PK_CFG=1..3
+typedef PkCfg<64, 16, 80, 20, 5, 1> PkOnePair;   // 16+1 warps, one pair per thread
+typedef PkCfg<64, 16, 72, 20, 6, 2> PkNarrowBox; // smaller box, deeper ring
+typedef PkCfg<64, 8, 80, 12, 8, 1> PkSmallTile;  // 64x8 tiles (small batches), 8+1 warps
+
+static int pk_cfg()
+{
+    static const int v = []() {
+        const char *e = getenv("MPIFLOW_PK_CFG");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
 static int tma_cfg()
 {
     static const int v = []() {
@@ -298,14 +363,17 @@ static int tma_cfg()
     return v;
 }
 
-// MPIFLOW_RENDER_PATH=generic forces the plain global-load kernel (debugging / A-B measurements)
-static bool tma_enabled()
+// MPIFLOW_RENDER_PATH = pk (default: persistent packed kernel) | tma (per-tile CTAs, scalar) | generic (plain
+// global loads); debugging / A-B measurements only -- tensors a path cannot take fall through to the next
+static int render_path()
 {
-    static const bool on = []() {
-        const char *v = getenv("MPIFLOW_RENDER_PATH");
-        return !(v && strcmp(v, "generic") == 0);
+    static const int v = []() {
+        const char *e = getenv("MPIFLOW_RENDER_PATH");
+        if (e && strcmp(e, "generic") == 0) return 2;
+        if (e && strcmp(e, "tma") == 0) return 1;
+        return 0;
     }();
-    return on;
+    return v;
 }
 
 MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
@@ -333,7 +401,8 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     PlaneConst *pc = reinterpret_cast<PlaneConst *>(workspace);
     BatchConst *bc = reinterpret_cast<BatchConst *>(reinterpret_cast<char *>(workspace) +
                                                     align_up((size_t)B * S * sizeof(PlaneConst), 256));
-    plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, bc, status);
+    int *tile_counter = reinterpret_cast<int *>(reinterpret_cast<char *>(bc) + align_up((size_t)B * sizeof(BatchConst), 256));
+    plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, bc, status, tile_counter);
     int rc = mf_launch_status();
     if (rc) return rc;
 
@@ -346,7 +415,19 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     p.out_rgb = out_rgb; p.out_depth = out_depth; p.out_mask = out_mask; p.out_flow = out_flow;
     p.out_obj = out_obj;
 
-    if (tma_enabled()) {
+    if (render_path() == 0) {
+        bool used = false;
+        static const bool force_literal = []() { const char *e = getenv("MPIFLOW_PK_FORCE_LITERAL"); return e && atoi(e) != 0; }();
+        if (force_literal) p.flags |= MF_FLAG_FORCE_LITERAL;
+        switch (pk_cfg()) {
+            case 1: rc = launch_pk<PkOnePair>(p, tile_counter, st, &used); break;
+            case 2: rc = launch_pk<PkNarrowBox>(p, tile_counter, st, &used); break;
+            case 3: rc = launch_pk<PkSmallTile>(p, tile_counter, st, &used); break;
+            default: rc = launch_pk<PkDefault>(p, tile_counter, st, &used); break;
+        }
+        if (rc || used) return rc;
+    }
+    if (render_path() <= 1) {
         bool used = false;
         switch (tma_cfg()) {
             case 1: rc = launch_tma<CfgFull>(p, st, &used); break;
@@ -379,5 +460,36 @@ MPIFLOW_API int mpiflow_debug_div_f32(const float *a, const float *c, const floa
 {
     MF_CHECK_ARG(a && c && b && qa && qc && n > 0);
     debug_div_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, c, b, n, qa, qc);
+    return mf_launch_status();
+}
+
+// test hook: the packed (f32x2) arithmetic of render_pk.cuh against the scalar IEEE operations, element-wise on
+// device arrays of even length n; out[k*n + i], k = 0..9: fma2, fma, mul2, mul, sub2, sub, floor-by-magic, floorf,
+// unfused a*b+c packed, scalar
+__global__ void debug_packed_kernel(const float *a, const float *b, const float *c, int n, float *out)
+{
+    const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i + 1 >= n) return;
+    const float2 A = make_float2(a[i], a[i + 1]), B = make_float2(b[i], b[i + 1]), C = make_float2(c[i], c[i + 1]);
+    const float2 f = __ffma2_rn(A, B, C), m = __fmul2_rn(A, pk(B.x)), d = __fadd2_rn(A, pkneg(C));
+    out[0 * n + i] = f.x; out[0 * n + i + 1] = f.y;
+    out[1 * n + i] = __fmaf_rn(A.x, B.x, C.x); out[1 * n + i + 1] = __fmaf_rn(A.y, B.y, C.y);
+    out[2 * n + i] = m.x; out[2 * n + i + 1] = m.y;
+    out[3 * n + i] = __fmul_rn(A.x, B.x); out[3 * n + i + 1] = __fmul_rn(A.y, B.x);
+    out[4 * n + i] = d.x; out[4 * n + i + 1] = d.y;
+    out[5 * n + i] = __fsub_rn(A.x, C.x); out[5 * n + i + 1] = __fsub_rn(A.y, C.y);
+    const float2 pos = make_float2(fabsf(A.x), fabsf(A.y));
+    const float2 t = __fadd2_rd(pos, pk(MF_MAGIC));
+    out[6 * n + i] = (float)(__float_as_uint(t.x) - MF_MAGIC_BITS); out[6 * n + i + 1] = (float)(__float_as_uint(t.y) - MF_MAGIC_BITS);
+    out[7 * n + i] = floorf(pos.x); out[7 * n + i + 1] = floorf(pos.y);
+    const float2 u = pk_mul_then_add(A, pk(B.x), pk(-1.f));
+    out[8 * n + i] = u.x; out[8 * n + i + 1] = u.y;
+    out[9 * n + i] = __fadd_rn(__fmul_rn(A.x, B.x), -1.f); out[9 * n + i + 1] = __fadd_rn(__fmul_rn(A.y, B.x), -1.f);
+}
+
+MPIFLOW_API int mpiflow_debug_packed_f32(const float *a, const float *b, const float *c, int n, float *out, void *stream)
+{
+    MF_CHECK_ARG(a && b && c && out && n > 0 && (n % 2) == 0);
+    debug_packed_kernel<<<(n / 2 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, b, c, n, out);
     return mf_launch_status();
 }
