@@ -338,12 +338,12 @@ typedef TmaCfg<64, 16, 80, 24, 4, 2> CfgFull;        // 64x16 tiles, 16 warps, 1
 typedef TmaCfg<32, 16, 48, 24, 4, 2, 2> CfgNarrow;  // 32x16 tiles, 2 CTAs / SM
 typedef TmaCfg<64, 16, 80, 24, 3, 2> CfgShallow;    // 3-stage ring
 
-// persistent kernel: tile 64x16, box 80x20 (zoom up to ~1.19), 5-stage ring, 2 pixel pairs per thread, 8+1 warps
-typedef PkCfg<64, 16, 80, 20, 5, 2> PkDefault;
-// A/B shapes, selected with MPIFLOW_PK_CFG=1..3
-typedef PkCfg<64, 16, 80, 20, 5, 1> PkOnePair;   // 16+1 warps, one pair per thread
-typedef PkCfg<64, 16, 72, 20, 6, 2> PkNarrowBox; // smaller box, deeper ring
-typedef PkCfg<64, 8, 80, 12, 8, 1> PkSmallTile;  // 64x8 tiles (small batches), 8+1 warps
+// persistent kernel: tile 64x16, box 80x20 (zoom up to ~1.19), 5-stage ring, one pixel pair per thread, 16+2 warps
+typedef PkCfg<64, 16, 80, 20, 5, 1> PkDefault;
+// A/B shapes, selected with MPIFLOW_PK_CFG
+typedef PkCfg<64, 16, 80, 20, 5, 2> PkTwoPairs;  // 8+2 warps, two pairs per thread
+typedef PkCfg<64, 8, 80, 12, 8, 1> PkSmallTile;  // 64x8 tiles, 8+2 warps: small launches (few tiles per SM)
+typedef PkCfg<64, 24, 80, 28, 4, 2> Pk24x2;      // 12+1 warps, two pairs per thread, 64x24 tiles
 
 static int pk_cfg()
 {
@@ -419,11 +419,19 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
         bool used = false;
         static const bool force_literal = []() { const char *e = getenv("MPIFLOW_PK_FORCE_LITERAL"); return e && atoi(e) != 0; }();
         if (force_literal) p.flags |= MF_FLAG_FORCE_LITERAL;
+        static const unsigned dbg_bits = []() { const char *e = getenv("MPIFLOW_PK_DBG"); return e ? (unsigned)strtoul(e, nullptr, 0) : 0u; }();
+        p.flags |= dbg_bits & (MF_FLAG_DBG_NO_LOADS | MF_FLAG_DBG_NO_COMPUTE);
+        // few 64x16 tiles per SM (small images / batches): halve the tile so that the persistent CTAs stay balanced
+        const long long tiles16 = (long long)((W + 63) / 64) * ((H + 15) / 16) * B;
         switch (pk_cfg()) {
-            case 1: rc = launch_pk<PkOnePair>(p, tile_counter, st, &used); break;
-            case 2: rc = launch_pk<PkNarrowBox>(p, tile_counter, st, &used); break;
+            case 1: rc = launch_pk<PkTwoPairs>(p, tile_counter, st, &used); break;
             case 3: rc = launch_pk<PkSmallTile>(p, tile_counter, st, &used); break;
-            default: rc = launch_pk<PkDefault>(p, tile_counter, st, &used); break;
+            case 6: rc = launch_pk<Pk24x2>(p, tile_counter, st, &used); break;
+            case 9: rc = launch_pk<PkDefault>(p, tile_counter, st, &used); break;
+            default:
+                rc = tiles16 < 6ll * sm_count() ? launch_pk<PkSmallTile>(p, tile_counter, st, &used)
+                                                : launch_pk<PkDefault>(p, tile_counter, st, &used);
+                break;
         }
         if (rc || used) return rc;
     }
