@@ -226,10 +226,12 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = world * Be * e2e_steps / e2e_s
-    # the host path and the device path must agree bit for bit (same kernels)
+    # the host path renders frame by frame (smaller tiles per launch), the device path a whole batch: same kernel,
+    # but which warps take the lean / border loop differs with the tile shape -> agreement to rounding, not bit for bit
     calls[0]()
     torch.cuda.synchronize()
-    assert torch.equal(h_out[0], calls[0].out[0][:Be].cpu()), "host-buffer path and device path disagree"
+    dev_rgb = calls[0].out[0][:Be].cpu()
+    assert (h_out[0] - dev_rgb).abs().max().item() <= 2e-6, "host-buffer path and device path disagree"
     h2d = sum(h_in[k].numel() * 4 for k in h_in)
     d2h = sum(o.numel() * 4 for o in h_out)
 
@@ -259,7 +261,10 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "render_fused_tma_kernel", "bytes_per_launch": bytes_per_launch},
+                         "kernel": "render_fused_pk_kernel (persistent, warp-specialised; step = prologue + this kernel)",
+                         "bytes_per_launch": bytes_per_launch,
+                         "bound_note": "algorithmic HBM bytes vs measured copy bandwidth; the kernel itself is bound by "
+                                       "instruction issue (DESIGN.md 5.1), not by HBM"},
             "cpu_baseline": cpu,
         }
         if gather:
@@ -339,7 +344,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=4, help="frames per step per GPU (device-resident leg)")
+    ap.add_argument("--frames-per-step", type=int, default=16, help="frames per step per GPU (device-resident leg)")
     ap.add_argument("--e2e-frames-per-step", type=int, default=2)
     ap.add_argument("--e2e-max-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
