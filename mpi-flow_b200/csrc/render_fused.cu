@@ -59,10 +59,25 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
         float mind = depth;
         for (int i = 1; i < S; i++) mind = fminf(mind, __frcp_rn(disparity[n + i]));
         bc.min_zc = mind + bc.a;   // NaN-propagating on purpose: a NaN disparity disables the lean loop
-        bc.pad = 0.f;
+        bc.hts_cols_invariant = 0.f;   // set by batch_flags_kernel
         bcs[b] = bc;
     }
     if (!(ok && okb) && status) atomicExch(status, 1);
+}
+
+// H_tgt_src = K_t (R + t n^T / d) K_s^-1 with n = (0,0,1): the plane enters through column 2 of the middle factor
+// only, so when row 2 of K_s^-1 is (0, 0, 1) columns 0 and 1 of the product do not depend on the plane -- in fp32 as
+// well.  Checked on the computed matrices, bit for bit, so that the lean plane loop may hoist h0 x + h1 y.
+__global__ void batch_flags_kernel(const PlaneConst *__restrict__ pc, BatchConst *__restrict__ bcs, int S)
+{
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const PlaneConst *p0 = pc + (size_t)b * S;
+    bool same = true;
+    for (int s = lane; s < S; s += 32)
+        for (int i = 0; i < 9; i++)
+            if (i % 3 != 2) same = same && (__float_as_uint(p0[s].hts[i]) == __float_as_uint(p0[0].hts[i]));
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) bcs[b].hts_cols_invariant = same ? 1.f : 0.f;
 }
 
 // front-to-back accumulator of one frame (mpi_rendering.py:79-96, :143-152)
@@ -404,6 +419,9 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     int *tile_counter = reinterpret_cast<int *>(reinterpret_cast<char *>(bc) + align_up((size_t)B * sizeof(BatchConst), 256));
     plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, bc, status, tile_counter);
     int rc = mf_launch_status();
+    if (rc) return rc;
+    batch_flags_kernel<<<B, 32, 0, st>>>(pc, bc, S);
+    rc = mf_launch_status();
     if (rc) return rc;
 
     RenderParams p;
