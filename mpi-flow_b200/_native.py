@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpiflow_sm100.so")
+# MPIFLOW_LIB: development override (A/B builds of the same library, tools/ab.py)
+LIB_PATH = os.environ.get("MPIFLOW_LIB") or os.path.join(_HERE, "libmpiflow_sm100.so")
 
 BG_DEPTH_INF = 1
 HARD_FLOW = 2
