@@ -358,6 +358,8 @@ typedef PkCfg<64, 16, 80, 20, 5, 1> PkDefault;
 // A/B shapes, selected with MPIFLOW_PK_CFG
 typedef PkCfg<64, 16, 80, 20, 5, 2> PkTwoPairs;  // 8+2 warps, two pairs per thread
 typedef PkCfg<64, 8, 80, 12, 8, 1> PkSmallTile;  // 64x8 tiles, 8+2 warps: small launches (few tiles per SM)
+typedef PkCfg<64, 16, 96, 20, 5, 1> PkWideBox;   // row pitch = 0 mod 32 banks: rows of a footprint never collide
+typedef PkCfg<64, 16, 72, 20, 6, 1> PkNarrowBox; // less overfetch, deeper ring
 typedef PkCfg<64, 24, 80, 28, 4, 2> Pk24x2;      // 12+1 warps, two pairs per thread, 64x24 tiles
 
 static int pk_cfg()
@@ -445,6 +447,8 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
             case 1: rc = launch_pk<PkTwoPairs>(p, tile_counter, st, &used); break;
             case 3: rc = launch_pk<PkSmallTile>(p, tile_counter, st, &used); break;
             case 6: rc = launch_pk<Pk24x2>(p, tile_counter, st, &used); break;
+            case 7: rc = launch_pk<PkWideBox>(p, tile_counter, st, &used); break;
+            case 8: rc = launch_pk<PkNarrowBox>(p, tile_counter, st, &used); break;
             case 9: rc = launch_pk<PkDefault>(p, tile_counter, st, &used); break;
             default:
                 rc = tiles16 < 6ll * sm_count() ? launch_pk<PkSmallTile>(p, tile_counter, st, &used)

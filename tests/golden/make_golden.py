@@ -52,6 +52,42 @@ def run_render(inp, keep_inputs, **flags):
     return out, (sampler, xyz_src, xyz_tgt)
 
 
+def load_reference_warpback():
+    """warpback/utils.py imports pytorch3d (absent here) at module level; its mesh-construction helpers are
+    plain torch.  Import the unmodified file with empty stand-ins for the three pytorch3d modules."""
+    import importlib.util
+    import types
+    for name, attrs in (("pytorch3d", ()), ("pytorch3d.renderer", ()), ("pytorch3d.renderer.mesh", ("rasterize_meshes",)),
+                        ("pytorch3d.structures", ("Meshes",)), ("pytorch3d.ops", ("interpolate_face_attributes",))):
+        m = sys.modules.setdefault(name, types.ModuleType(name))
+        for a in attrs:
+            setattr(m, a, None)
+    spec = importlib.util.spec_from_file_location("ref_warpback_utils", os.path.join(REF, "warpback", "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def warpback_fixture():
+    ref = load_reference_warpback()
+    g = torch.Generator().manual_seed(synth.SEED)
+    b, h, w = 2, 12, 20
+    rgbd = torch.rand((b, 4, h, w), generator=g)
+    rgbd[:, 3, :, w // 2:] *= 0.3                     # a depth discontinuity for the visibility mask
+    cam_int = torch.tensor([[0.58, 0, 0.5], [0, 0.58, 0.5], [0, 0, 1]]).repeat(b, 1, 1)
+    cam_int[1, 0, 0] = 0.7
+    r = ref.RGBDRenderer(torch.device("cpu"))
+    mesh = r.construct_mesh(rgbd, cam_int)
+    aa = torch.tensor([[[0.01, -0.02, 0.005]], [[0.0, 0.03, -0.01]]])
+    tt = torch.tensor([[[0.1, -0.05, -0.15]], [[-0.2, 0.0, 0.05]]])
+    save("warpback", rgbd=rgbd.numpy(), cam_int=cam_int.numpy(), vertice=mesh["vertice"].numpy(),
+         faces=mesh["faces"].numpy(), attributes=mesh["attributes"].numpy(), size=np.array(mesh["size"]),
+         pixel=r.get_screen_pixel_coord(h, w).numpy(), persp=r.get_perspective_from_intrinsic(cam_int).numpy(),
+         vis=r.get_visible_mask(rgbd.permute(0, 2, 3, 1)[..., -1:]).numpy(), aa=aa.numpy(), tt=tt.numpy(),
+         pose=ref.transformation_from_parameters(aa, tt).numpy(),
+         pose_inv=ref.transformation_from_parameters(aa, tt, invert=True).numpy())
+
+
 def save(name, **arrs):
     p = os.path.join(HERE, name + ".npz")
     np.savez_compressed(p, **arrs)
@@ -59,6 +95,9 @@ def save(name, **arrs):
 
 
 def main():
+    if "--warpback-only" in sys.argv:
+        warpback_fixture()
+        return
     # ---- whole-frame cases (inputs regenerable from synth + the stored meta) ------------------
     cases = {
         # name: (B, S, H, W, kind, pose, seed, flags)
@@ -136,6 +175,7 @@ def main():
         out = mpi_oracle.forward_warping(src, idx, idy, z, use_ref=True)
         splat.update({f"{tag}_meta": np.array([h, w, seed], np.int64), f"{tag}_mode": mode, f"{tag}_warped": out})
     save("splat", **splat)
+    warpback_fixture()
 
 
 if __name__ == "__main__":
