@@ -6,7 +6,8 @@
 //     rgb(T)       = src[k_m],  m = max{ i : z_i < z_{i-1} }          (untouched if no such i)
 //     valid(T)     = 1 iff n >= 1
 //     collision(T) = 1 iff z_{n-1} == 1000   (n == 1, or the previous writer's z was exactly 1000)
-// Parallel restatement: stable LSD radix sort of the source pixels by target index (stability keeps
+// Parallel restatement: stable LSD radix sort (wide digits, two passes up to 4 M pixels) of the source pixels by
+// target index (stability keeps
 // raster order inside a segment) -> every writer sees its predecessor in the sorted array -> winners
 // are marked independently, the last winner per target is an atomicMax over sorted positions.
 // Everything is integer except the single fp32 '<', so the result is deterministic.
@@ -18,8 +19,11 @@
 
 namespace {
 
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
+// LSD radix sort with wide digits: 2 passes of <= 11 bits sort up to 4 M pixels (3 passes beyond).  Per pass two
+// launches: a per-digit scan of the per-block histograms, and the stable scatter, which also accumulates the
+// histogram of the NEXT pass (by destination block) so that the keys are read once per pass.
+constexpr int MAX_DIGIT_BITS = 11;
+constexpr int MAX_RADIX = 1 << MAX_DIGIT_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ROUNDS = 8;                                   // items per thread
@@ -27,47 +31,84 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;            // items per bl
 
 // key = target raster index (y*w + x), narrowed through int exactly like warping.c:16-17;
 // out-of-range targets (undefined behaviour in the reference) get the sentinel n and are dropped.
-__global__ void splat_keys_kernel(const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h,
-                                  int w, uint32_t n, uint32_t *__restrict__ keys,
-                                  uint32_t *__restrict__ vals, uint32_t *__restrict__ winpos)
-{
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int x = (int)idx[k], y = (int)idy[k];
-    const bool ok = (x >= 0) && (x < w) && (y >= 0) && (y < h);
-    keys[k] = ok ? (uint32_t)y * (uint32_t)w + (uint32_t)x : n;
-    vals[k] = k;
-    winpos[k] = 0;
-}
-
+// Also: histogram of the first digit per block (digit-major, block-minor), winpos = 0, and zeroing of the
+// histograms of the later passes (the scatter kernels add to them).
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t nblocks,
-                  uint32_t *__restrict__ hist)
+splat_keys_hist_kernel(const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h, int w, uint32_t n,
+                       int digit_bits, uint32_t nblocks, uint32_t *__restrict__ keys, uint32_t *__restrict__ winpos,
+                       uint32_t *__restrict__ hist0, uint32_t *__restrict__ hist_later, uint32_t hist_later_count)
 {
-    __shared__ uint32_t sh[RADIX];
-    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) sh[i] = 0;
+    extern __shared__ uint32_t sh[];
+    const uint32_t radix = 1u << digit_bits;
+    for (uint32_t i = threadIdx.x; i < radix; i += SORT_THREADS) sh[i] = 0;
+    for (uint32_t i = blockIdx.x * SORT_THREADS + threadIdx.x; i < hist_later_count; i += gridDim.x * SORT_THREADS)
+        hist_later[i] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * SORT_TILE;
     for (int r = 0; r < SORT_ROUNDS; r++) {
-        const uint32_t i = base + r * SORT_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (RADIX - 1)], 1u);
+        const uint32_t k = base + r * SORT_THREADS + threadIdx.x;
+        if (k < n) {
+            const int x = (int)idx[k], y = (int)idy[k];
+            const bool ok = (x >= 0) && (x < w) && (y >= 0) && (y < h);
+            const uint32_t key = ok ? (uint32_t)y * (uint32_t)w + (uint32_t)x : n;
+            keys[k] = key;
+            winpos[k] = 0;
+            atomicAdd(&sh[key & (radix - 1)], 1u);
+        }
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = sh[d];
+    for (uint32_t d = threadIdx.x; d < radix; d += SORT_THREADS) hist0[(size_t)d * nblocks + blockIdx.x] = sh[d];
 }
 
-// exclusive scan of hist (digit-major, block-minor) by a single block
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *__restrict__ hist, uint32_t total)
+// one warp per digit: exclusive scan of that digit's per-block counts (in place) and the digit's total
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_offsets_kernel(uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t radix, uint32_t *__restrict__ totals)
 {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < total; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = (i < total) ? hist[i] : 0;
+    const uint32_t d = blockIdx.x * SORT_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (d >= radix) return;
+    uint32_t *row = hist + (size_t)d * nblocks;
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 32) {
+        const uint32_t b = b0 + lane;
+        const uint32_t v = (b < nblocks) ? row[b] : 0;
         uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (b < nblocks) row[b] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) totals[d] = carry;
+}
+
+// stable scatter: item order inside a tile is (warp, round, lane); ranks come from match_any.
+// FIRST: values are the item indices themselves (nothing to read); hist_next != nullptr: count the next digit
+// per destination block.
+template <bool FIRST>
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t n,
+                     int shift, int digit_bits, uint32_t nblocks, const uint32_t *__restrict__ offsets,
+                     const uint32_t *__restrict__ totals, uint32_t *__restrict__ keys_out,
+                     uint32_t *__restrict__ vals_out, uint32_t *__restrict__ hist_next, int next_shift,
+                     int next_bits)
+{
+    extern __shared__ uint32_t sh[];
+    const uint32_t radix = 1u << digit_bits, mask = radix - 1;
+    uint32_t *cnt = sh;                        // [SORT_WARPS][radix]
+    uint32_t *dbase = sh + SORT_WARPS * radix; // [radix] exclusive scan of the digit totals
+    __shared__ uint32_t warp_sums[SORT_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < SORT_WARPS * radix; i += SORT_THREADS) cnt[i] = 0;
+    {   // digit bases: block-wide exclusive scan of totals[0..radix), radix / 256 consecutive digits per thread
+        const uint32_t per = radix / SORT_THREADS ? radix / SORT_THREADS : 1;
+        const uint32_t d0 = threadIdx.x * per;
+        uint32_t local = 0;
+        for (uint32_t i = 0; i < per; i++)
+            if (d0 + i < radix) local += totals[d0 + i];
+        uint32_t inc = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -75,33 +116,11 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t *__restrict__
         }
         if (lane == 31) warp_sums[wid] = inc;
         __syncthreads();
-        if (wid == 0) {
-            uint32_t ws = warp_sums[lane], winc = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            warp_sums[lane] = winc - ws;  // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        if (i < total) hist[i] = carry + warp_sums[wid] + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_sums[wid] + inc;
-        __syncthreads();
+        uint32_t before = inc - local;
+        for (int wv = 0; wv < wid; wv++) before += warp_sums[wv];
+        for (uint32_t i = 0; i < per; i++)
+            if (d0 + i < radix) { dbase[d0 + i] = before; before += totals[d0 + i]; }
     }
-}
-
-// stable scatter: item order inside a tile is (warp, round, lane); ranks come from match_any
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t n,
-                     int shift, uint32_t nblocks, const uint32_t *__restrict__ offsets,
-                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out)
-{
-    __shared__ uint32_t cnt[SORT_WARPS][RADIX];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t wbase = blockIdx.x * SORT_TILE + wid * (SORT_ROUNDS * 32);
     uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS];
@@ -110,22 +129,22 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         const uint32_t i = wbase + r * 32 + lane;
         const bool live = i < n;
         key[r] = live ? keys_in[i] : 0xffffffffu;
-        val[r] = live ? vals_in[i] : 0;
+        val[r] = FIRST ? i : (live ? vals_in[i] : 0);
         const unsigned act = __ballot_sync(0xffffffffu, live);
         if (live) {
-            const uint32_t d = (key[r] >> shift) & (RADIX - 1);
+            const uint32_t d = (key[r] >> shift) & mask;
             const unsigned peers = __match_any_sync(act, d);
-            if (lane == __ffs(peers) - 1) cnt[wid][d] += __popc(peers);
+            if (lane == __ffs(peers) - 1) cnt[wid * radix + d] += __popc(peers);
         }
         __syncwarp();
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {
-        uint32_t run = offsets[(size_t)d * nblocks + blockIdx.x];
+    for (uint32_t d = threadIdx.x; d < radix; d += SORT_THREADS) {
+        uint32_t run = dbase[d] + offsets[(size_t)d * nblocks + blockIdx.x];
 #pragma unroll
         for (int wv = 0; wv < SORT_WARPS; wv++) {
-            const uint32_t c = cnt[wv][d];
-            cnt[wv][d] = run;
+            const uint32_t c = cnt[wv * radix + d];
+            cnt[wv * radix + d] = run;
             run += c;
         }
     }
@@ -136,13 +155,15 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         const bool live = i < n;
         const unsigned act = __ballot_sync(0xffffffffu, live);
         if (live) {
-            const uint32_t d = (key[r] >> shift) & (RADIX - 1);
+            const uint32_t d = (key[r] >> shift) & mask;
             const unsigned peers = __match_any_sync(act, d);
-            const uint32_t pos = cnt[wid][d] + __popc(peers & ((1u << lane) - 1));
+            const uint32_t pos = cnt[wid * radix + d] + __popc(peers & ((1u << lane) - 1));
             keys_out[pos] = key[r];
             vals_out[pos] = val[r];
+            if (hist_next)
+                atomicAdd(&hist_next[(size_t)((key[r] >> next_shift) & ((1u << next_bits) - 1)) * nblocks + pos / SORT_TILE], 1u);
             __syncwarp(act);
-            if (lane == __ffs(peers) - 1) cnt[wid][d] += __popc(peers);
+            if (lane == __ffs(peers) - 1) cnt[wid * radix + d] += __popc(peers);
         }
         __syncwarp();
     }
@@ -183,18 +204,27 @@ __global__ void splat_rgb_kernel(const uint32_t *__restrict__ vals, const uint32
 inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct SplatLayout {
-    size_t keysA, valsA, keysB, valsB, winpos, hist, total;
+    size_t keysA, valsA, keysB, valsB, winpos, hist, totals, total;
     uint32_t nblocks;
+    int passes, digit_bits;
+    size_t hist_stride;   // uint32 per pass
     SplatLayout(size_t n)
     {
         nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+        int bits = 0;
+        while ((n >> bits) != 0) bits++;  // keys are in [0, n]
+        passes = (bits + MAX_DIGIT_BITS - 1) / MAX_DIGIT_BITS;
+        if (passes < 1) passes = 1;
+        digit_bits = (bits + passes - 1) / passes;
+        hist_stride = (size_t)(1u << digit_bits) * nblocks;
         size_t o = 0;
         keysA = o; o += al256(n * 4);
         valsA = o; o += al256(n * 4);
         keysB = o; o += al256(n * 4);
         valsB = o; o += al256(n * 4);
         winpos = o; o += al256(n * 4);
-        hist = o; o += al256((size_t)RADIX * nblocks * 4);
+        hist = o; o += al256(hist_stride * passes * 4);
+        totals = o; o += al256((size_t)MAX_RADIX * 4);
         total = o;
     }
 };
@@ -225,13 +255,30 @@ MPIFLOW_API int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx,
     uint32_t *winpos = (uint32_t *)(ws + L.winpos), *hist = (uint32_t *)(ws + L.hist);
     const unsigned g256 = (n + 255) / 256;
 
-    splat_keys_kernel<<<g256, 256, 0, st>>>(idx, idy, h, w, n, kA, vA, winpos);
-    int bits = 0;
-    while ((n >> bits) != 0) bits++;  // keys are in [0, n]
-    for (int shift = 0; shift < bits; shift += RADIX_BITS) {
-        radix_hist_kernel<<<L.nblocks, SORT_THREADS, 0, st>>>(kA, n, shift, L.nblocks, hist);
-        radix_scan_kernel<<<1, 1024, 0, st>>>(hist, RADIX * L.nblocks);
-        radix_scatter_kernel<<<L.nblocks, SORT_THREADS, 0, st>>>(kA, vA, n, shift, L.nblocks, hist, kB, vB);
+    uint32_t *totals = (uint32_t *)(ws + L.totals);
+    const int db = L.digit_bits;
+    const uint32_t radix = 1u << db;
+    const size_t scatter_smem = (size_t)(SORT_WARPS + 1) * radix * sizeof(uint32_t);
+    static std::once_flag attr_once;
+    std::call_once(attr_once, []() {
+        const int big = (SORT_WARPS + 1) * MAX_RADIX * (int)sizeof(uint32_t);
+        cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    });
+    splat_keys_hist_kernel<<<L.nblocks, SORT_THREADS, radix * sizeof(uint32_t), st>>>(
+        idx, idy, h, w, n, db, L.nblocks, kA, winpos, hist, hist + L.hist_stride,
+        (uint32_t)(L.hist_stride * (L.passes - 1)));
+    for (int p = 0; p < L.passes; p++) {
+        uint32_t *hp = hist + (size_t)p * L.hist_stride;
+        const bool more = p + 1 < L.passes;
+        radix_offsets_kernel<<<(radix + SORT_WARPS - 1) / SORT_WARPS, SORT_THREADS, 0, st>>>(hp, L.nblocks, radix, totals);
+        if (p == 0)
+            radix_scatter_kernel<true><<<L.nblocks, SORT_THREADS, scatter_smem, st>>>(
+                kA, nullptr, n, 0, db, L.nblocks, hp, totals, kB, vB, more ? hp + L.hist_stride : nullptr, db, db);
+        else
+            radix_scatter_kernel<false><<<L.nblocks, SORT_THREADS, scatter_smem, st>>>(
+                kA, vA, n, p * db, db, L.nblocks, hp, totals, kB, vB, more ? hp + L.hist_stride : nullptr,
+                (p + 1) * db, db);
         uint32_t *t = kA; kA = kB; kB = t;
         t = vA; vA = vB; vB = t;
     }
