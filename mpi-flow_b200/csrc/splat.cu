@@ -123,18 +123,19 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     }
     __syncthreads();
     const uint32_t wbase = blockIdx.x * SORT_TILE + wid * (SORT_ROUNDS * 32);
-    uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS];
+    uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS], peer[SORT_ROUNDS];   // peer: lanes of this round with the same digit
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t i = wbase + r * 32 + lane;
         const bool live = i < n;
         key[r] = live ? keys_in[i] : 0xffffffffu;
         val[r] = FIRST ? i : (live ? vals_in[i] : 0);
+        peer[r] = 0;
         const unsigned act = __ballot_sync(0xffffffffu, live);
         if (live) {
             const uint32_t d = (key[r] >> shift) & mask;
-            const unsigned peers = __match_any_sync(act, d);
-            if (lane == __ffs(peers) - 1) cnt[wid * radix + d] += __popc(peers);
+            peer[r] = __match_any_sync(act, d);
+            if (lane == __ffs(peer[r]) - 1) cnt[wid * radix + d] += __popc(peer[r]);
         }
         __syncwarp();
     }
@@ -156,7 +157,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         const unsigned act = __ballot_sync(0xffffffffu, live);
         if (live) {
             const uint32_t d = (key[r] >> shift) & mask;
-            const unsigned peers = __match_any_sync(act, d);
+            const unsigned peers = peer[r];
             const uint32_t pos = cnt[wid * radix + d] + __popc(peers & ((1u << lane) - 1));
             keys_out[pos] = key[r];
             vals_out[pos] = val[r];
