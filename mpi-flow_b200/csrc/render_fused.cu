@@ -45,7 +45,8 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
     c.depth = depth;
     c.ddepth = (s + 1 < S) ? __fsub_rn(__frcp_rn(disparity[n + 1]), depth) : 0.f;
     c.ddepth_l2e = c.ddepth * 1.4426950408889634f;
-    c.pad[0] = c.pad[1] = 0.f;
+    c.depth_next = (s + 1 < S) ? __frcp_rn(disparity[n + 1]) : depth;
+    c.pad = 0.f;
     pc[n] = c;
     bool okb = true;
     if (s == 0) {
@@ -120,15 +121,14 @@ render_fused_kernel(const RenderParams p)
     const float rW = __frcp_rn(Wf * 0.5f), rH = __frcp_rn(Hf * 0.5f);
     const size_t HW = (size_t)H * W, q = (size_t)y * W + x;
 
-    // source-frame ray length |Kinv (x,y,1)|: xyz_src = ray * depth (mpi_rendering.py:234-236), so
-    // the spacing of consecutive planes along it is |ray| * (depth[s+1] - depth[s])   (:104-107)
-    float vnorm;
+    // source-frame ray Kinv (x,y,1): xyz_src = fl(ray * depth) (mpi_rendering.py:234-236); the spacing of
+    // consecutive planes is evaluated from those products, like the reference (:104-107)
+    float ray0, ray1, ray2;
     {
         const float *k = p.bc[b].kinv;
-        const float v0 = mf_dot3(__ldg(k + 0), __ldg(k + 1), __ldg(k + 2), xf, yf);
-        const float v1 = mf_dot3(__ldg(k + 3), __ldg(k + 4), __ldg(k + 5), xf, yf);
-        const float v2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
-        vnorm = sqrtf(fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
+        ray0 = mf_dot3(__ldg(k + 0), __ldg(k + 1), __ldg(k + 2), xf, yf);
+        ray1 = mf_dot3(__ldg(k + 3), __ldg(k + 4), __ldg(k + 5), xf, yf);
+        ray2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
     }
 
     const float *rgb_b = p.rgb + (size_t)b * p.rgb_sb;
@@ -185,8 +185,12 @@ render_fused_kernel(const RenderParams p)
         float tu, tv;
         mf_div2(U, V, Q, tu, tv);
         const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf);  // :212-218
-        const float dist_s = (s + 1 < S) ? vnorm * c.ddepth : 1e3f;
-        const float Ts = __expf(-__ldg(sig_s + q) * dist_s);
+        // thickness literally: |fl(ray * depth[s+1]) - fl(ray * depth[s])|; transmittance with the reference's expf
+        const float ex = __fsub_rn(__fmul_rn(ray0, c.depth_next), __fmul_rn(ray0, c.depth));
+        const float ey = __fsub_rn(__fmul_rn(ray1, c.depth_next), __fmul_rn(ray1, c.depth));
+        const float ez = __fsub_rn(__fmul_rn(ray2, c.depth_next), __fmul_rn(ray2, c.depth));
+        const float dist_s = (s + 1 < S) ? sqrtf(__fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)))) : 1e3f;
+        const float Ts = expf(__fmul_rn(-__ldg(sig_s + q), dist_s));
         const float ws = acc_s * (1.f - Ts);
         acc_s *= (Ts + 1e-6f);
         if (hard) {  // one-hot of the first arg-max weight (:126-130)
@@ -495,7 +499,7 @@ MPIFLOW_API int mpiflow_debug_div_f32(const float *a, const float *c, const floa
 
 // test hook: the packed (f32x2) arithmetic of render_pk.cuh against the scalar IEEE operations, element-wise on
 // device arrays of even length n; out[k*n + i], k = 0..9: fma2, fma, mul2, mul, sub2, sub, floor-by-magic, floorf,
-// unfused a*b+c packed, scalar
+// unfused a*b+c packed, scalar, packed expf clone of -|a|/30, expf of the same, packed sqrt of |a*b|, sqrtf
 __global__ void debug_packed_kernel(const float *a, const float *b, const float *c, int n, float *out)
 {
     const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
@@ -515,6 +519,14 @@ __global__ void debug_packed_kernel(const float *a, const float *b, const float 
     const float2 u = pk_mul_then_add(A, pk(B.x), pk(-1.f));
     out[8 * n + i] = u.x; out[8 * n + i + 1] = u.y;
     out[9 * n + i] = __fadd_rn(__fmul_rn(A.x, B.x), -1.f); out[9 * n + i + 1] = __fadd_rn(__fmul_rn(A.y, B.x), -1.f);
+    const float2 xe = make_float2(-fabsf(A.x) * (1.f / 30.f), -fabsf(A.y) * (1.f / 30.f));
+    const float2 ee = pk_expf_nonpos(xe);
+    out[10 * n + i] = ee.x; out[10 * n + i + 1] = ee.y;
+    out[11 * n + i] = expf(xe.x); out[11 * n + i + 1] = expf(xe.y);
+    const float2 qa = make_float2(fabsf(A.x * B.x), fabsf(A.y * B.y));
+    const float2 qs = pk_sqrt_rn(qa);
+    out[12 * n + i] = qs.x; out[12 * n + i + 1] = qs.y;
+    out[13 * n + i] = sqrtf(fmaxf(qa.x, 1e-30f)); out[13 * n + i + 1] = sqrtf(fmaxf(qa.y, 1e-30f));
 }
 
 MPIFLOW_API int mpiflow_debug_packed_f32(const float *a, const float *b, const float *c, int n, float *out, void *stream)

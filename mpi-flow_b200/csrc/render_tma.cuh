@@ -227,7 +227,7 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
     const float *sig_b = p.sigma + (size_t)b * p.sig_sb;
     const float *obj_b = HAS_OBJ ? p.obj + (size_t)b * p.obj_sb : nullptr;
 
-    float yf[PPT], vnorm[PPT], tdist[PPT], invb[PPT];
+    float yf[PPT], ray0[PPT], ray1[PPT], ray2[PPT], tdist[PPT], invb[PPT];
     uint32_t sd_off[PPT];  // byte offset of the pixel's un-warped sigma inside a stage
     const float bc_a = bc.a;
     const uint32_t stage0_u32 = smem_u32(stage_buf);
@@ -242,7 +242,7 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
         const float v0 = mf_dot3(bc.kinv[0], bc.kinv[1], bc.kinv[2], xf, yf[j]);
         const float v1 = mf_dot3(bc.kinv[3], bc.kinv[4], bc.kinv[5], xf, yf[j]);
         const float v2 = mf_dot3(bc.kinv[6], bc.kinv[7], bc.kinv[8], xf, yf[j]);
-        vnorm[j] = sqrtf(fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
+        ray0[j] = v0; ray1[j] = v1; ray2[j] = v2;
         // target-frame ray r = Kt^-1 (x,y,1); plane s is hit at depth Z_s = (d_s + a) / b(q) with
         // a = (R^T t)_z, b(q) = (R^T r)_z; consecutive hits are |r| |d[s+1]-d[s]| / |b| apart
         const float r0 = mf_dot3(bc.ktinv[0], bc.ktinv[1], bc.ktinv[2], xf, yf[j]);
@@ -396,7 +396,12 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
                     mf_div2(U, V, Q, tu, tv);
                     const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf[j]);
                     const float sgs = lds_f32<0>(stage_u32 + sd_off[j]);  // un-warped sigma of plane s
-                    const float Ts = fast_ex2(-sgs * fmaf(vnorm[j], dmul, dadd));
+                    // source-frame thickness and transmittance literally (mpi_rendering.py:104-120): see render_pk.cuh
+                    const float ex = __fsub_rn(__fmul_rn(ray0[j], c.depth_next), __fmul_rn(ray0[j], c.depth));
+                    const float ey = __fsub_rn(__fmul_rn(ray1[j], c.depth_next), __fmul_rn(ray1[j], c.depth));
+                    const float ez = __fsub_rn(__fmul_rn(ray2[j], c.depth_next), __fmul_rn(ray2[j], c.depth));
+                    const float ds = last ? 1e3f : sqrtf(__fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex))));
+                    const float Ts = expf(__fmul_rn(-sgs, ds));
                     const float ws = q.acc_s * (1.f - Ts);
                     q.acc_s *= (Ts + 1e-6f);
                     if (HARD) {  // one-hot of the first arg-max weight (:126-130)
