@@ -269,7 +269,7 @@ def run_ours(args, rank, local_rank, world):
         }
         if gather:
             line["with_output_gather"] = gather
-        print(json.dumps(line), flush=True)
+        OUT.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -335,10 +335,32 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
+
+
+class QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there as well (NCCL prints its version banner at
+    communicator creation): while the benchmark runs, file descriptor 1 points at stderr; emit() restores it for
+    the single line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
+OUT = None
 
 
 def main():
+    global OUT
+    OUT = QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
