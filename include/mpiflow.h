@@ -78,7 +78,7 @@ int mpiflow_debug_div_f32(const float *a, const float *c, const float *b, int n,
 
 /* test hook: packed fp32x2 arithmetic of the persistent renderer next to the scalar IEEE operations; n even,
  * out [14,n]: rows fma2, fma, mul2, mul, sub2, sub, floor via 2^23 (round-down add), floorf, unfused a*b-1
- * packed, scalar, packed clone of libdevice expf on -|a|/30, expf of the same,
+ * packed, scalar, packed clone of libdevice expf on -|a|/22, expf of the same,
  * packed IEEE sqrt of |a*b|, sqrtf of the same */
 int mpiflow_debug_packed_f32(const float *a, const float *b, const float *c, int n, float *out, void *stream);
 
