@@ -88,6 +88,25 @@ def warpback_fixture():
          pose_inv=ref.transformation_from_parameters(aa, tt, invert=True).numpy())
 
 
+def flow_io_fixture():
+    """bytes written by the reference's write_flow.py for a seeded flow field"""
+    import importlib.util
+    import tempfile
+    spec = importlib.util.spec_from_file_location("ref_write_flow", os.path.join(REF, "write_flow.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(synth.SEED)
+    flow = ((rng.random((11, 17, 2)) - 0.5) * 300).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        ref.writeFlow(os.path.join(d, "a.flo"), flow)
+        ref.writeFlowKITTI(os.path.join(d, "a.png"), flow)
+        flo = np.fromfile(os.path.join(d, "a.flo"), np.uint8)
+        png = np.fromfile(os.path.join(d, "a.png"), np.uint8)
+        kf, kv = ref.readFlowKITTI(os.path.join(d, "a.png"))
+        back = ref.readFlow(os.path.join(d, "a.flo"))
+    save("flow_io", flow=flow, flo_bytes=flo, kitti_png_bytes=png, kitti_flow=kf, kitti_valid=kv, flo_back=back)
+
+
 def save(name, **arrs):
     p = os.path.join(HERE, name + ".npz")
     np.savez_compressed(p, **arrs)
@@ -97,6 +116,9 @@ def save(name, **arrs):
 def main():
     if "--warpback-only" in sys.argv:
         warpback_fixture()
+        return
+    if "--flow-io-only" in sys.argv:
+        flow_io_fixture()
         return
     # ---- whole-frame cases (inputs regenerable from synth + the stored meta) ------------------
     cases = {
@@ -176,6 +198,7 @@ def main():
         splat.update({f"{tag}_meta": np.array([h, w, seed], np.int64), f"{tag}_mode": mode, f"{tag}_warped": out})
     save("splat", **splat)
     warpback_fixture()
+    flow_io_fixture()
 
 
 if __name__ == "__main__":
