@@ -137,6 +137,21 @@ int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx, const int64
                              uint8_t *warped, int h, int w, void *workspace, size_t workspace_bytes,
                              void *stream);
 
+/* ---- mesh rasteriser behind warpback.utils.RGBDRenderer.render_mesh ----------------
+ * Replaces pytorch3d.renderer.mesh.rasterize_meshes(faces_per_pixel=1, blur_radius) followed by
+ * pytorch3d.ops.interpolate_face_attributes (reference warpback/utils.py:56-63).  PARITY UNPINNED: pytorch3d is an
+ * un-vendored dependency (0.6.2, README.md:30) absent from this image; the kernels follow its published naive
+ * rasteriser and are checked against oracle/raster_oracle.py.
+ *   verts_ndc [B,V,3] (x, y in pytorch3d NDC: +X left, +Y up, shorter image side spans [-1,1]; z = depth > 0)
+ *   faces [B,F,3] int64 vertex indices, attrs [B,V,C]
+ *   out [B,C,H,W] interpolated attributes (0 where no face), pix_to_face [B,H,W] int64 (b*F + f, -1 = none),
+ *   zbuf [B,H,W], bary [B,H,W,3]  -- each may be NULL
+ *   workspace: mpiflow_rasterize_workspace_bytes(B, H, W) bytes, 8-byte aligned */
+size_t mpiflow_rasterize_workspace_bytes(int B, int H, int W);
+int mpiflow_rasterize_mesh_f32(const float *verts_ndc, const int64_t *faces, const float *attrs, int B, int V, int F,
+                               int C, int H, int W, float blur_radius, float *out, int64_t *pix_to_face,
+                               float *zbuf, float *bary, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

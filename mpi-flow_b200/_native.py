@@ -41,6 +41,8 @@ _SIGNATURES = {
     "mpiflow_forward_warp_host": (_I, [_P, _P, _P, _P, _P, _I, _I]),
     "mpiflow_forward_warp_workspace_bytes": (_SZ, [_I, _I]),
     "mpiflow_forward_warp_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
+    "mpiflow_rasterize_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "mpiflow_rasterize_mesh_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
