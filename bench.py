@@ -127,7 +127,7 @@ class FusedCall:
         self.B = B
         new = lambda c: torch.empty((B, c, H, W), dtype=torch.float32, device=device)
         self.out = (new(3), new(1), new(1), new(2), new(1))
-        self.ws_bytes = self.L.mpiflow_render_workspace_bytes(B, S)
+        self.ws_bytes = self.L.mpiflow_render_workspace_bytes_hw(B, S, H, W)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.d = d

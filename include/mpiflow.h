@@ -60,9 +60,12 @@ int mpiflow_plane_homographies_f32(const float *G, const float *Kinv, const floa
  *   disparity [B,S] (dense), G [B,4,4], Kinv [B,3,3], Kt [B,3,3]
  *   out_rgb [B,3,H,W], out_depth [B,1,H,W], out_mask [B,1,H,W] (count of valid planes, :347),
  *   out_flow [B,2,H,W] (flowA2B, source frame), out_obj [B,1,H,W]      -- all dense
- *   workspace: mpiflow_render_workspace_bytes(B, S) bytes, device, 16-byte aligned
+ *   workspace: mpiflow_render_workspace_bytes(B, S) bytes, device, 16-byte aligned; with
+ *     mpiflow_render_workspace_bytes_hw(B, S, H, W) bytes (S*H*W floats more) launches of 4 or more frames whose
+ *     K_src^-1 and disparities agree evaluate the source-frame plane spacing once per launch instead of per frame
  *   status: device int (may be NULL), non-zero when a homography was singular */
 size_t mpiflow_render_workspace_bytes(int B, int S);
+size_t mpiflow_render_workspace_bytes_hw(int B, int S, int H, int W);
 int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
                              const float *sigma, int64_t sig_sb, int64_t sig_ss,
                              const float *obj, int64_t obj_sb, int64_t obj_ss,

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "mpiflow_error_string": (_c.c_char_p, [_I]),
     "mpiflow_plane_homographies_f32": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P]),
     "mpiflow_render_workspace_bytes": (_SZ, [_I, _I]),
+    "mpiflow_render_workspace_bytes_hw": (_SZ, [_I, _I, _I, _I]),
     "mpiflow_render_fused_f32": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P,
                                       _I, _I, _I, _I, _U, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
     "mpiflow_debug_div_f32": (_I, [_P, _P, _P, _I, _P, _P, _P]),

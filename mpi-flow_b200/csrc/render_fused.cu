@@ -61,6 +61,8 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
         for (int i = 1; i < S; i++) mind = fminf(mind, __frcp_rn(disparity[n + i]));
         bc.min_zc = mind + bc.a;   // NaN-propagating on purpose: a NaN disparity disables the lean loop
         bc.hts_cols_invariant = 0.f;   // set by batch_flags_kernel
+        bc.spacing_table = 0.f;        // set by batch_flags_kernel
+        bc.pad[0] = bc.pad[1] = bc.pad[2] = 0.f;
         bcs[b] = bc;
     }
     if (!(ok && okb) && status) atomicExch(status, 1);
@@ -69,16 +71,50 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
 // H_tgt_src = K_t (R + t n^T / d) K_s^-1 with n = (0,0,1): the plane enters through column 2 of the middle factor
 // only, so when row 2 of K_s^-1 is (0, 0, 1) columns 0 and 1 of the product do not depend on the plane -- in fp32 as
 // well.  Checked on the computed matrices, bit for bit, so that the lean plane loop may hoist h0 x + h1 y.
-__global__ void batch_flags_kernel(const PlaneConst *__restrict__ pc, BatchConst *__restrict__ bcs, int S)
+__global__ void batch_flags_kernel(const PlaneConst *__restrict__ pc, BatchConst *__restrict__ bcs, int S, int have_table)
 {
     const int b = blockIdx.x, lane = threadIdx.x;
     const PlaneConst *p0 = pc + (size_t)b * S;
-    bool same = true;
-    for (int s = lane; s < S; s += 32)
+    bool same = true, shared = have_table != 0;
+    for (int s = lane; s < S; s += 32) {
         for (int i = 0; i < 9; i++)
             if (i % 3 != 2) same = same && (__float_as_uint(p0[s].hts[i]) == __float_as_uint(p0[0].hts[i]));
+        // source-frame plane spacing depends on K_src^-1 and the plane depths only: the table of entry 0 serves entry b
+        shared = shared && (__float_as_uint(p0[s].depth) == __float_as_uint(pc[s].depth)) &&
+                 (__float_as_uint(p0[s].depth_next) == __float_as_uint(pc[s].depth_next));
+    }
+    if (lane < 9) shared = shared && (__float_as_uint(bcs[b].kinv[lane]) == __float_as_uint(bcs[0].kinv[lane]));
     same = __all_sync(0xffffffffu, same);
-    if (lane == 0) bcs[b].hts_cols_invariant = same ? 1.f : 0.f;
+    shared = __all_sync(0xffffffffu, shared);
+    if (lane == 0) {
+        bcs[b].hts_cols_invariant = same ? 1.f : 0.f;
+        bcs[b].spacing_table = shared ? 1.f : 0.f;
+    }
+}
+
+// Plane spacing of the source frame for batch entry 0, table[s][y][x] = | fl(ray * depth[s+1]) - fl(ray * depth[s]) |
+// (1e3 for the last plane, mpi_rendering.py:104-120), with exactly the operations of the plane loop of render_pk.cuh.
+// It depends on K_src^-1 and the plane depths only -- in the generator both are the same for every frame -- so one
+// launch computes it once (0.13 GB at 1280x384x64, a few microseconds per frame) instead of per frame and plane.
+__global__ void spacing_table_kernel(const PlaneConst *__restrict__ pc, const BatchConst *__restrict__ bcs, int S, int H,
+                                     int W, float *__restrict__ table)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const float xf = (float)x, yf = (float)y;
+    const float *k = bcs[0].kinv;
+    const float r0 = mf_dot3(__ldg(k + 0), __ldg(k + 1), __ldg(k + 2), xf, yf);
+    const float r1 = mf_dot3(__ldg(k + 3), __ldg(k + 4), __ldg(k + 5), xf, yf);
+    const float r2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
+    const size_t HW = (size_t)H * W, q = (size_t)y * W + x;
+    for (int s = 0; s < S; s++) {
+        const float dn = __ldg(&pc[s].depth_next), da = __ldg(&pc[s].depth);
+        const float ex = __fsub_rn(__fmul_rn(r0, dn), __fmul_rn(r0, da));
+        const float ey = __fsub_rn(__fmul_rn(r1, dn), __fmul_rn(r1, da));
+        const float ez = __fsub_rn(__fmul_rn(r2, dn), __fmul_rn(r2, da));
+        const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+        table[(size_t)s * HW + q] = (s + 1 == S) ? 1e3f : sqrtf(fmaxf(e2, 1e-30f));
+    }
 }
 
 // front-to-back accumulator of one frame (mpi_rendering.py:79-96, :143-152)
@@ -224,6 +260,14 @@ MPIFLOW_API size_t mpiflow_render_workspace_bytes(int B, int S)
     return align_up((size_t)B * S * sizeof(PlaneConst), 256) + align_up((size_t)B * sizeof(BatchConst), 256) + 256;
 }
 
+// the same plus room for the [S,H,W] plane-spacing table (see spacing_table_kernel): a launch that gets this much
+// workspace evaluates the source-frame plane spacing once instead of per frame
+MPIFLOW_API size_t mpiflow_render_workspace_bytes_hw(int B, int S, int H, int W)
+{
+    if (B <= 0 || S <= 0 || H <= 0 || W <= 0) return 0;
+    return mpiflow_render_workspace_bytes(B, S) + align_up((size_t)S * H * W * sizeof(float), 256);
+}
+
 // ---- TMA path ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -262,7 +306,7 @@ static bool make_map(CUtensorMap *m, const float *ptr, int rank, const uint64_t 
 }
 
 struct RenderMaps {
-    CUtensorMap rgb, sig, obj, sigd;
+    CUtensorMap rgb, sig, obj, sigd, dist;
 };
 
 // tensor maps over the caller's planar tensors: rgb (W,H,3,S,B) box (bw,bh,3), sigma / mask (W,H,S,B) box
@@ -294,6 +338,12 @@ static bool make_render_maps(const RenderParams &p, uint32_t bw, uint32_t bh, ui
         if (!make_map(&m->obj, p.obj, 4, d, sb, bw, bh, 1)) return false;
     } else {
         m->obj = m->sig;
+    }
+    m->dist = m->sigd;
+    if (p.spacing_table) {   // [S,H,W] table of batch entry 0, one tile per (tile, plane)
+        const uint64_t d[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)S};
+        const uint64_t sb[2] = {w4, hw4};
+        if (!make_map(&m->dist, p.spacing_table, 3, d, sb, tw, th, 1)) return false;
     }
     return true;
 }
@@ -344,7 +394,7 @@ static int launch_pk(const RenderParams &p, int *tile_counter, cudaStream_t st, 
     if (e != cudaSuccess) return (int)e;
     const long long ntiles = (long long)((p.W + Cfg::TW - 1) / Cfg::TW) * ((p.H + Cfg::TH - 1) / Cfg::TH) * p.B;
     const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-    kern<<<grid, Cfg::THREADS, smem, st>>>(m.rgb, m.sig, m.obj, m.sigd, p, tile_counter);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(m.rgb, m.sig, m.obj, m.sigd, m.dist, p, tile_counter);
     *used = true;
     return mf_launch_status();
 }
@@ -364,7 +414,7 @@ typedef PkCfg<64, 16, 80, 20, 5, 2> PkTwoPairs;  // 8+2 warps, two pairs per thr
 typedef PkCfg<64, 8, 80, 12, 8, 1> PkSmallTile;  // 64x8 tiles, 8+2 warps: small launches (few tiles per SM)
 typedef PkCfg<64, 16, 96, 20, 5, 1> PkWideBox;   // row pitch = 0 mod 32 banks: rows of a footprint never collide
 typedef PkCfg<64, 16, 72, 20, 6, 1> PkNarrowBox; // less overfetch, deeper ring
-typedef PkCfg<64, 24, 80, 28, 4, 2> Pk24x2;      // 12+1 warps, two pairs per thread, 64x24 tiles
+typedef PkCfg<64, 24, 80, 28, 3, 2> Pk24x2;      // 12+1 warps, two pairs per thread, 64x24 tiles
 
 static int pk_cfg()
 {
@@ -426,9 +476,22 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, bc, status, tile_counter);
     int rc = mf_launch_status();
     if (rc) return rc;
-    batch_flags_kernel<<<B, 32, 0, st>>>(pc, bc, S);
+    // Source-frame plane spacing once per launch instead of per frame and plane (spacing_table_kernel): when the caller
+    // gave room for the table (mpiflow_render_workspace_bytes_hw), the launch is large enough to amortise it, and TMA
+    // can describe it.  Entries whose K_src^-1 or plane depths differ from entry 0 evaluate it in the plane loop.
+    static const bool table_off = []() { const char *e = getenv("MPIFLOW_PK_SPACING_TABLE"); return e && atoi(e) == 0; }();
+    const size_t base_bytes = mpiflow_render_workspace_bytes(B, S);
+    const bool have_table = !table_off && render_path() == 0 && B >= 4 && (W % 4) == 0 &&
+                            workspace_bytes >= mpiflow_render_workspace_bytes_hw(B, S, H, W);
+    float *table = have_table ? reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + base_bytes) : nullptr;
+    batch_flags_kernel<<<B, 32, 0, st>>>(pc, bc, S, have_table ? 1 : 0);
     rc = mf_launch_status();
     if (rc) return rc;
+    if (have_table) {
+        spacing_table_kernel<<<dim3((W + 127) / 128, H), 128, 0, st>>>(pc, bc, S, H, W, table);
+        rc = mf_launch_status();
+        if (rc) return rc;
+    }
 
     RenderParams p;
     p.rgb = rgb; p.rgb_sb = rgb_sb; p.rgb_ss = rgb_ss; p.rgb_sc = rgb_sc;
@@ -438,6 +501,7 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     p.B = B; p.S = S; p.H = H; p.W = W; p.flags = flags;
     p.out_rgb = out_rgb; p.out_depth = out_depth; p.out_mask = out_mask; p.out_flow = out_flow;
     p.out_obj = out_obj;
+    p.spacing_table = table;
 
     if (render_path() == 0) {
         bool used = false;

@@ -213,7 +213,7 @@ def render_fused(mpi_rgb_src, mpi_sigma_src, mpi_disparity_src, G_tgt_src, K_src
         out = (new(3), new(1), new(1), new(2), new(1) if obj is not None else None)
     o_rgb, o_depth, o_mask, o_flow, o_obj = out
     L = nat.lib()
-    ws_bytes = L.mpiflow_render_workspace_bytes(B, S)
+    ws_bytes = L.mpiflow_render_workspace_bytes_hw(B, S, H, W) if B >= 4 else L.mpiflow_render_workspace_bytes(B, S)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
     nat.check(L.mpiflow_render_fused_f32(
