@@ -155,6 +155,26 @@ int mpiflow_rasterize_mesh_f32(const float *verts_ndc, const int64_t *faces, con
                                int C, int H, int W, float blur_radius, float *out, int64_t *pix_to_face,
                                float *zbuf, float *bary, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- sample assembly around the renderer (utils/utils.py:159-288) -----------------------
+ * mpiflow_blend_src_f32 replaces the source-view mpi_rendering.render call and the blend of the photograph into the
+ * plane colours (utils/utils.py:183-204): out[b,s,c] = w * src_img[b,c] + (1 - w) * rgb[b,s,c] with
+ * w = blend_weights[b,s] = prod_{j<s} (exp(-sigma_j * dist_j) + 1e-6) in the source frame.  One pass: 4 S channels
+ * read, 3 S written, no xyz / weight tensors.
+ *   rgb / sigma: strided as in mpiflow_render_fused_f32; src_img [B,3,H,W]; disparity [B,S]; Kinv [B,3,3]
+ *   out_rgb [B,S,3,H,W] dense; may be the rgb buffer itself when that is dense (each element is read once, before
+ *   its write, by the same thread) */
+int mpiflow_blend_src_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc, const float *sigma,
+                          int64_t sig_sb, int64_t sig_ss, const float *src_img, const float *disparity,
+                          const float *Kinv, int B, int S, int H, int W, float *out_rgb, void *stream);
+/* mpiflow_assemble_sample_f32 replaces the host-side thresholds and merges of the two renders of one sample
+ * (utils/utils.py:241-283, flow clip :347): frame/mask/flow = outputs of the render with obj_mask, *_dync = outputs
+ * of the render with 1 - obj_mask; all channel-planar fp32 [3|1|2,H,W]; obj_mask [H,W].
+ *   flow_mix f32 [H,W,2]; frame_mix u8 [H,W,3] in B,G,R order (holes 255); fill_mask u8 [H,W] (1 = to inpaint) */
+int mpiflow_assemble_sample_f32(const float *frame, const float *frame_dync, const float *mask,
+                                const float *mask_dync, const float *flow, const float *flow_dync,
+                                const float *obj_mask, float mask_thresh, int H, int W, float *flow_mix,
+                                unsigned char *frame_mix, unsigned char *fill_mask, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

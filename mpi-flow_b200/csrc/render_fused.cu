@@ -317,23 +317,27 @@ static bool make_render_maps(const RenderParams &p, uint32_t bw, uint32_t bh, ui
     if ((W % 4) != 0) return false;
     const uint64_t w4 = (uint64_t)W * 4, hw4 = (uint64_t)H * W * 4;
     {
-        const uint64_t d[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)S, (uint64_t)B};
+        // a batch stride of 0 (one MPI under several poses) is a batch extent of 1; the kernels then ask for entry 0
+        const bool one = B == 1 || p.rgb_sb == 0;
+        const uint64_t d[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)S, (uint64_t)(one ? 1 : B)};
         const uint64_t sb[4] = {w4, (uint64_t)p.rgb_sc * 4, (uint64_t)(S > 1 ? p.rgb_ss : p.rgb_sc * 3) * 4,
-                                (uint64_t)(B > 1 ? p.rgb_sb : (int64_t)hw4) * (B > 1 ? 4 : 1)};
+                                (uint64_t)(one ? (int64_t)hw4 : p.rgb_sb * 4)};
         if (p.rgb_sc <= 0 || p.rgb_ss < 0 || p.rgb_sb < 0) return false;
         if (!make_map(&m->rgb, p.rgb, 5, d, sb, bw, bh, 3)) return false;
     }
     {
-        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)S, (uint64_t)B};
-        const uint64_t sb[3] = {w4, (uint64_t)(S > 1 ? p.sig_ss * 4 : (int64_t)hw4), (uint64_t)(B > 1 ? p.sig_sb * 4 : (int64_t)hw4)};
+        const bool one = B == 1 || p.sig_sb == 0;
+        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)S, (uint64_t)(one ? 1 : B)};
+        const uint64_t sb[3] = {w4, (uint64_t)(S > 1 ? p.sig_ss * 4 : (int64_t)hw4), (uint64_t)(one ? (int64_t)hw4 : p.sig_sb * 4)};
         if (p.sig_ss < 0 || p.sig_sb < 0) return false;
         if (!make_map(&m->sig, p.sigma, 4, d, sb, bw, bh, 1)) return false;
         if (!make_map(&m->sigd, p.sigma, 4, d, sb, tw, th, 1)) return false;
     }
     if (p.obj) {
         const bool shared_mask = (p.obj_ss == 0) || S == 1;
-        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)(shared_mask ? 1 : S), (uint64_t)B};
-        const uint64_t sb[3] = {w4, (uint64_t)(shared_mask ? (int64_t)hw4 : p.obj_ss * 4), (uint64_t)(B > 1 ? p.obj_sb * 4 : (int64_t)hw4)};
+        const bool one = B == 1 || p.obj_sb == 0;
+        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)(shared_mask ? 1 : S), (uint64_t)(one ? 1 : B)};
+        const uint64_t sb[3] = {w4, (uint64_t)(shared_mask ? (int64_t)hw4 : p.obj_ss * 4), (uint64_t)(one ? (int64_t)hw4 : p.obj_sb * 4)};
         if (p.obj_ss < 0 || p.obj_sb < 0) return false;
         if (!make_map(&m->obj, p.obj, 4, d, sb, bw, bh, 1)) return false;
     } else {

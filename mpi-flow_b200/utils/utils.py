@@ -1,0 +1,155 @@
+"""Sample assembly -- drop-in for the rendering half of MPI-Flow's utils/utils.py (gen_swing_path :55,
+render_novel_view :65, generate_random_pose :121, render_3dphoto_dynamic :159, render_novel_view_dynamic :291;
+same names, positional orders and return tuples).  SURVEY.md 8(f) row 1.
+
+One dataset sample is, on the device:
+  1. mpiflow_blend_src_f32       source-view transmittance + blend of the photograph into the plane colours
+                                 (reference: get_src_xyz + render + three BxSx3xHxW temporaries, :183-204)
+  2. mpiflow_render_fused_f32    BOTH poses of the sample in one launch: the MPI is passed once with a batch stride
+                                 of 0, the poses and the two masks (obj, 1 - obj) are per frame; frames of the same
+                                 tile are neighbours in the tile queue so the second one finds its boxes in L2
+                                 (reference: two render_novel_view_dynamic calls, :210-238)
+  3. mpiflow_assemble_sample_f32 flow clip, thresholds, merges, u8 conversion (reference: numpy on the host after
+                                 eight device->host copies, :239-283)
+and only flow_mix, frame_mix and fill_mask cross PCIe.  Hole filling stays cv2.inpaint on the host (:284-286),
+outside the path.  No CPU fallback: tensors must live on a CUDA device.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+
+import _native as nat
+from geometry import transformation_from_parameters
+from utils.mpi import mpi_rendering
+from utils.mpi.homography_sampler import HomographySample
+
+
+def gen_swing_path(num_frames=90, r_x=0.14, r_y=0.0, r_z=0.10):
+    """Tuple of num_frames 4x4 camera poses on the 3D-photo swing; reference :55-62."""
+    phase = 2.0 * math.pi * (torch.arange(num_frames) / (num_frames - 1))
+    poses = torch.eye(4).repeat(num_frames, 1, 1)
+    poses[:, 0, 3] = r_x * torch.sin(phase)
+    poses[:, 1, 3] = r_y * torch.cos(phase)
+    poses[:, 2, 3] = r_z * (torch.cos(phase) - 1.0)
+    return poses.unbind()
+
+
+def generate_random_pose(ext_cz, base_motions=[0.1, 0.1, 0.1], device="cuda"):
+    """Random camera (base_motions 0.1) or object (base_motions 0) motion as a 4x4 matrix; reference :121-156.
+    Draws from the `random` module in the reference's order, so a seeded run picks the same poses."""
+    sign = lambda: (-1) ** random.randrange(2)
+    sx, sy, sz = sign(), sign(), sign()
+    if base_motions[0] == 0.1:
+        sz = -1                       # cameras move forward
+    else:
+        sx, sy, sz = sx * 0.5, sy * 0.5, sz * 0.5
+    tx = (random.random() * 0.1 + base_motions[0]) * sx
+    ty = (random.random() * 0.1 + base_motions[1]) * sy
+    tz = (random.random() * ext_cz + base_motions[2]) * sz
+    ax_s, ay_s, az_s = sign(), sign(), sign()
+    ax = (random.random() * math.pi / 36.0) * ax_s
+    ay = (random.random() * math.pi / 36.0) * ay_s
+    az = (random.random() * math.pi / 36.0) * az_s
+    axisangle = torch.from_numpy(np.array([[[ax * 0.4, ay * 0.4, az * 0.4]]], dtype=np.float32)).to(device).float()
+    translation = torch.from_numpy(np.array([[[tx, ty, tz]]])).to(device).float()
+    return transformation_from_parameters(axisangle, translation)[0]
+
+
+def _batched(m, B, n):
+    m = m if m.dim() == 3 else m.unsqueeze(0)
+    return m.expand(B, n, n)
+
+
+def render_novel_view(mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, G_tgt_src, K_src_inv, K_tgt, K_src,
+                      src_pose, homography_sampler, hard_flow=False):
+    """-> (tgt_imgs_syn, tgt_depth_syn, flow_syn); reference :65-118.  K_src, src_pose and the sampler are unused by
+    the arithmetic there as well (the per-plane flow volume it builds is discarded by render_tgt_rgb_depth)."""
+    B = mpi_all_rgb_src.shape[0]
+    rgb, depth, _, flow, _ = mpi_rendering.render_fused(
+        mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, _batched(G_tgt_src, B, 4), K_src_inv, K_tgt,
+        None, False, hard_flow)
+    return rgb, depth, flow
+
+
+def render_novel_view_dynamic(obj_mask, mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, G_tgt_src, K_src_inv,
+                              K_tgt, K_src, src_pose, homography_sampler, hard_flow=False):
+    """-> (tgt_imgs_syn, tgt_depth_syn, flow_syn clipped to +-200, obj_mask warped and composited);
+    reference :291-348."""
+    B = mpi_all_rgb_src.shape[0]
+    rgb, depth, _, flow, obj = mpi_rendering.render_fused(
+        mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, _batched(G_tgt_src, B, 4), K_src_inv, K_tgt,
+        obj_mask, False, hard_flow)
+    return rgb, depth, torch.clip(flow, -200, 200), obj
+
+
+def blend_src_into_mpi(src_imgs, mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, k_src_inv):
+    """blend_weights * src + (1 - blend_weights) * rgb with the source-view blend_weights of the MPI; reference
+    :183-204 -> BxSx3xHxW fp32."""
+    B, S, _, H, W = mpi_all_rgb_src.shape
+    rgb, sig = nat.dev(mpi_all_rgb_src, "mpi_all_rgb_src"), nat.dev(mpi_all_sigma_src, "mpi_all_sigma_src")
+    if not nat.inner_contiguous(rgb):
+        rgb = rgb.contiguous()
+    if not nat.inner_contiguous(sig):
+        sig = sig.contiguous()
+    src = nat.dev(src_imgs, "src_imgs").expand(B, 3, H, W).contiguous()
+    disp = nat.dev(disparity_all_src, "disparity_all_src").contiguous()
+    kinv = nat.dev(k_src_inv.to(rgb.device), "k_src_inv").expand(B, 3, 3).contiguous()
+    out = torch.empty((B, S, 3, H, W), dtype=torch.float32, device=rgb.device)
+    nat.check(nat.lib().mpiflow_blend_src_f32(
+        nat.ptr(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), nat.ptr(sig), sig.stride(0), sig.stride(1),
+        nat.ptr(src), nat.ptr(disp), nat.ptr(kinv), B, S, H, W, nat.ptr(out), nat.stream(rgb)))
+    return out
+
+
+def render_sample_pair(src_imgs, obj_mask, mpi_all_src, disparity_all_src, k_src, k_tgt, cam_ext, cam_ext_dynamic,
+                       hard_flow=False, mask_thresh=0.99, k_src_inv=None):
+    """The device part of render_3dphoto_dynamic for given poses (cam_ext moves the masked object, cam_ext_dynamic
+    the rest).  -> device tensors (flow_mix HxWx2 f32, frame_mix HxWx3 u8 BGR, fill_mask HxW u8) plus the two raw
+    renders (rgb 2x3xHxW, obj 2x1xHxW, flow 2x2xHxW) for inspection.  k_src_inv: the fp64-inverted intrinsics if the
+    caller already has them (the reference inverts on the host for every sample, which costs a device sync)."""
+    if mpi_all_src.shape[0] != 1:
+        raise ValueError("one sample at a time, like the reference (it reads index 0 of every output)")
+    _, S, _, H, W = mpi_all_src.shape
+    device = mpi_all_src.device
+    if k_src_inv is None:
+        k_src_inv = torch.inverse(k_src.to(torch.float64).cpu()).to(device).to(k_src.dtype)  # :186-187
+    mpi_rgb, mpi_sigma = mpi_all_src[:, :, 0:3], mpi_all_src[:, :, 3:]
+    blended = blend_src_into_mpi(src_imgs, mpi_rgb, mpi_sigma, disparity_all_src, k_src_inv)
+    obj = nat.dev(obj_mask, "obj_mask").reshape(1, 1, H, W)
+    masks = torch.cat((obj, 1 - obj), 0).reshape(2, 1, 1, H, W)                            # :212, :226
+    poses = torch.stack((cam_ext.to(device).float(), cam_ext_dynamic.to(device).float()), 0)
+    rgb2, _, _, flow2, obj2 = mpi_rendering.render_fused(
+        blended.expand(2, S, 3, H, W), nat.dev(mpi_sigma).expand(2, S, 1, H, W), disparity_all_src.expand(2, S),
+        poses, k_src_inv.expand(2, 3, 3), k_tgt.expand(2, 3, 3), masks, False, hard_flow)
+    flow_mix = torch.empty((H, W, 2), dtype=torch.float32, device=device)
+    frame_mix = torch.empty((H, W, 3), dtype=torch.uint8, device=device)
+    fill_mask = torch.empty((H, W), dtype=torch.uint8, device=device)
+    obj_c = obj.contiguous()
+    nat.check(nat.lib().mpiflow_assemble_sample_f32(
+        nat.ptr(rgb2[0]), nat.ptr(rgb2[1]), nat.ptr(obj2[0]), nat.ptr(obj2[1]), nat.ptr(flow2[0]), nat.ptr(flow2[1]),
+        nat.ptr(obj_c), float(mask_thresh), H, W, nat.ptr(flow_mix), nat.ptr(frame_mix), nat.ptr(fill_mask),
+        nat.stream(rgb2)))
+    return flow_mix, frame_mix, fill_mask, (rgb2, obj2, flow2)
+
+
+def render_3dphoto_dynamic(opt, src_imgs, obj_mask, disp, mpi_all_src, disparity_all_src, k_src, k_tgt,
+                           data_path=None, name=None, hard_flow=False, mask_thresh=0.99):
+    """One training pair from one MPI: -> (flow_mix HxWx2 f32, src_np HxWx3 u8 BGR, inpainted HxWx3 u8 BGR, None);
+    reference :159-288.  `disp`, `data_path` and `name` are unused there too (name only has its suffix cut)."""
+    import cv2  # host-side hole filling only; outside the device path
+
+    if name is not None:
+        name = name.split(".")[0]
+    src_np = (nat.dev(src_imgs, "src_imgs")[0].permute(1, 2, 0) * 255).round().clamp(0, 255).to(torch.uint8)
+    src_np = src_np.flip(-1).contiguous().cpu().numpy()                                     # :173-177
+    device = mpi_all_src.device
+    cam_ext_dynamic = generate_random_pose(opt.ext_cz, device=device)                       # :206-208, same draw order
+    cam_ext = generate_random_pose(opt.ext_cz, base_motions=[0, 0, 0], device=device)
+    flow_mix, frame_mix, fill_mask, _ = render_sample_pair(
+        src_imgs, obj_mask, mpi_all_src, disparity_all_src, k_src, k_tgt, cam_ext, cam_ext_dynamic, hard_flow,
+        mask_thresh)
+    flow_mix, frame_mix, fill_mask = flow_mix.cpu().numpy(), frame_mix.cpu().numpy(), fill_mask.cpu().numpy()
+    inpainted = cv2.inpaint(frame_mix, fill_mask, 3, cv2.INPAINT_NS)                        # :284-286
+    return flow_mix, src_np, inpainted, None

@@ -107,6 +107,63 @@ def flow_io_fixture():
     save("flow_io", flow=flow, flo_bytes=flo, kitti_png_bytes=png, kitti_flow=kf, kitti_valid=kv, flo_back=back)
 
 
+def load_reference_utils():
+    """utils/utils.py imports moving_obj, which loads a prebuilt external/forward_warping/libwarping.so relative to
+    the working directory at import time (moving_obj.py:12).  The sample-assembly functions never call it, so the
+    unmodified file is imported with an empty stand-in for that one module."""
+    import importlib
+    import types
+    if "moving_obj" not in sys.modules:
+        m = types.ModuleType("moving_obj")
+        m.moveing_object_with_mask = None
+        sys.modules["moving_obj"] = m
+    return importlib.import_module("utils.utils")
+
+
+def sample_fixture():
+    """render_3dphoto_dynamic (utils/utils.py:159-288) on one small seeded sample, with the intermediates its two
+    render_novel_view_dynamic calls and its cv2.inpaint call see."""
+    import random
+    import types
+    ru = load_reference_utils()
+    B, S, H, W, seed = 1, 6, 40, 64, 114530
+    inp = synth.frame_inputs(B, S, H, W, "smooth", "random", seed)
+    mpi = inp["mpi"].copy()
+    mpi[:, :, 3] *= 4.0                       # opaque enough that both threshold branches occur
+    rng = np.random.default_rng(seed)
+    src = rng.random((B, 3, H, W), dtype=np.float32)
+    obj = (inp["obj_mask"] > 0.45).astype(np.float32) * 0.995 + inp["obj_mask"] * 0.005   # mostly hard, soft rim
+    calls, inpaint_args = [], []
+    real_rnvd, real_inpaint = ru.render_novel_view_dynamic, ru.cv2.inpaint
+
+    def spy_rnvd(obj_mask, rgb, sigma, disp, G, *rest, **kw):
+        out = real_rnvd(obj_mask, rgb, sigma, disp, G, *rest, **kw)
+        calls.append(dict(G=G.numpy().copy(), blended=rgb.numpy().copy(), frame=out[0].numpy(), flow=out[2].numpy(),
+                          mask=out[3].numpy()))
+        return out
+
+    def spy_inpaint(img, mask, *a):
+        inpaint_args.append((img.copy(), mask.copy()))
+        return real_inpaint(img, mask, *a)
+
+    ru.render_novel_view_dynamic = spy_rnvd
+    ru.cv2 = types.SimpleNamespace(inpaint=spy_inpaint, INPAINT_NS=ru.cv2.INPAINT_NS)
+    random.seed(seed)
+    opt = types.SimpleNamespace(ext_cz=0.15)
+    flow_mix, src_np, inpainted, _ = ru.render_3dphoto_dynamic(
+        opt, T(src), T(obj), None, T(mpi), T(inp["disparity"]), T(inp["K"]), T(inp["K"]), name="sample.png")
+    assert len(calls) == 2 and len(inpaint_args) == 1
+    save("sample_pair", meta=np.array([B, S, H, W, seed], np.int64), ext_cz=0.15, mask_thresh=0.99,
+         in_mpi=mpi, in_src=src, in_obj=obj, in_disparity=inp["disparity"], in_K=inp["K"],
+         G_obj=calls[0]["G"], G_cam=calls[1]["G"], blended=calls[0]["blended"],
+         frame=calls[0]["frame"], frame_dync=calls[1]["frame"], flow=calls[0]["flow"], flow_dync=calls[1]["flow"],
+         mask=calls[0]["mask"], mask_dync=calls[1]["mask"],
+         frame_mix=inpaint_args[0][0], fill_mask=inpaint_args[0][1],
+         flow_mix=flow_mix, src_np=src_np, inpainted=inpainted)
+    print("holes:", int(inpaint_args[0][1].sum()), "of", H * W, " own:", int((calls[0]["mask"] >= 0.99).sum()),
+          " obj>=t:", int((obj >= 0.99).sum()))
+
+
 def save(name, **arrs):
     p = os.path.join(HERE, name + ".npz")
     np.savez_compressed(p, **arrs)
@@ -116,6 +173,9 @@ def save(name, **arrs):
 def main():
     if "--warpback-only" in sys.argv:
         warpback_fixture()
+        return
+    if "--sample-only" in sys.argv:
+        sample_fixture()
         return
     if "--flow-io-only" in sys.argv:
         flow_io_fixture()
@@ -199,6 +259,7 @@ def main():
     save("splat", **splat)
     warpback_fixture()
     flow_io_fixture()
+    sample_fixture()
 
 
 if __name__ == "__main__":
