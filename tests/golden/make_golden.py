@@ -164,6 +164,66 @@ def sample_fixture():
           " obj>=t:", int((obj >= 0.99).sum()))
 
 
+def moving_obj_fixture():
+    """moveing_object_with_mask (moving_obj.py:16-175) on one small seeded case.  The module loads
+    external/forward_warping/libwarping.so relative to the working directory at import time (:12); it is imported
+    from a scratch directory where that path is the reference's warping.c built from source (oracle/_ref).  Its
+    call of the splat is wrapped to record the index maps, depth and result it passes by pointer (:127-129)."""
+    import ctypes
+    import importlib.util
+    import random
+    import tempfile
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libwarping_ref.so")
+    assert os.path.exists(ref_so), "run `make -C oracle ref` first"
+    sys.modules.pop("moving_obj", None)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as scratch:
+        os.makedirs(os.path.join(scratch, "external", "forward_warping"))
+        os.makedirs(os.path.join(scratch, "temp"))
+        os.symlink(ref_so, os.path.join(scratch, "external", "forward_warping", "libwarping.so"))
+        os.chdir(scratch)
+        try:
+            # by path: the drop-in of the same name in mpi-flow_b200/ is ahead of the reference on sys.path here
+            spec = importlib.util.spec_from_file_location("moving_obj", os.path.join(REF, "moving_obj.py"))
+            mo = importlib.util.module_from_spec(spec)
+            assert sys.modules["geometry"] is ref_geometry
+            spec.loader.exec_module(mo)
+            h, w, seed = 36, 60, 114540
+            rng = np.random.default_rng(seed)
+            yy, xx = np.mgrid[0:h, 0:w]
+            disp = (0.15 + 0.5 * (yy / h) + 0.2 * np.exp(-((xx - 25) ** 2 + (yy - 18) ** 2) / 60.0)).astype(np.float32)
+            disp += (rng.random((h, w), dtype=np.float32) - 0.5) * 0.02
+            inst = (((xx - 25) ** 2 + (yy - 18) ** 2) < 81).astype(np.float32)
+            rgb = rng.integers(0, 256, (h, w, 3)).astype(np.uint8)
+            K = synth.intrinsics(h, w)
+            Kinv = synth.intrinsics_inv(K)
+            rec = {}
+            real = mo.warp
+
+            def spy(src, idx, idy, z, warped, hh, ww):
+                n = hh.value * ww.value
+                rec["safe_x"] = np.ctypeslib.as_array((ctypes.c_int64 * n).from_address(idx.value)).copy()
+                rec["safe_y"] = np.ctypeslib.as_array((ctypes.c_int64 * n).from_address(idy.value)).copy()
+                rec["z"] = np.ctypeslib.as_array((ctypes.c_float * n).from_address(z.value)).copy()
+                rec["img"] = np.ctypeslib.as_array((ctypes.c_uint8 * (3 * n)).from_address(src.value)).copy()
+                real(src, idx, idy, z, warped, hh, ww)
+                rec["warped"] = np.ctypeslib.as_array((ctypes.c_uint8 * (5 * n)).from_address(warped.value)).copy()
+
+            mo.warp = spy
+            random.seed(seed)
+            mo.moveing_object_with_mask(None, T(disp)[None, None], rgb, T(K), T(Kinv), T(inst)[None, None], 0)
+            rec["next_random"] = random.random()      # where the reference leaves the `random` stream
+        finally:
+            os.chdir(cwd)
+            sys.modules.pop("moving_obj", None)
+    save("moving_obj", meta=np.array([h, w, seed], np.int64), in_disp=disp, in_inst=inst, in_rgb=rgb, in_K=K, in_Kinv=Kinv,
+         safe_x=rec["safe_x"].reshape(h, w), safe_y=rec["safe_y"].reshape(h, w), z=rec["z"].reshape(h, w),
+         img=rec["img"].reshape(h, w, 3), warped=rec["warped"].reshape(h, w, 5), next_random=rec["next_random"])
+    moved = (rec["safe_x"].reshape(h, w) != xx) | (rec["safe_y"].reshape(h, w) != yy)
+    print("moved pixels:", int(moved.sum()), " valid:", int(rec["warped"].reshape(h, w, 5)[..., 3].sum()),
+          " collisions flagged:", int(rec["warped"].reshape(h, w, 5)[..., 4].sum()))
+
+
 def save(name, **arrs):
     p = os.path.join(HERE, name + ".npz")
     np.savez_compressed(p, **arrs)
@@ -173,6 +233,9 @@ def save(name, **arrs):
 def main():
     if "--warpback-only" in sys.argv:
         warpback_fixture()
+        return
+    if "--moving-obj-only" in sys.argv:
+        moving_obj_fixture()
         return
     if "--sample-only" in sys.argv:
         sample_fixture()
@@ -260,6 +323,7 @@ def main():
     warpback_fixture()
     flow_io_fixture()
     sample_fixture()
+    moving_obj_fixture()
 
 
 if __name__ == "__main__":
