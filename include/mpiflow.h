@@ -34,6 +34,10 @@ extern "C" {
 /* render flags (keyword arguments of mpi_rendering.render_tgt_rgb_depth, mpi_rendering.py:259-272) */
 #define MPIFLOW_BG_DEPTH_INF 1u /* is_bg_depth_inf */
 #define MPIFLOW_HARD_FLOW 2u    /* hard_flow */
+/* n consecutive frames of the batch render the same MPI under n poses (utils/utils.py:210-238 renders every sample
+ * twice): rgb / sigma then hold B/n MPIs, rgb_sb / sig_sb step between MPIs, everything else stays per frame.
+ * n = 1..256, B % n == 0.  (A batch stride of 0 says the same for "all B frames share one MPI".) */
+#define MPIFLOW_POSES_PER_MPI(n) ((((unsigned)(n) - 1u) & 0xffu) << 8)
 
 int mpiflow_version(void);
 /* static string for any code returned by this library */

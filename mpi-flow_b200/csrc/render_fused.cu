@@ -167,8 +167,8 @@ render_fused_kernel(const RenderParams p)
         ray2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
     }
 
-    const float *rgb_b = p.rgb + (size_t)b * p.rgb_sb;
-    const float *sig_b = p.sigma + (size_t)b * p.sig_sb;
+    const float *rgb_b = p.rgb + (size_t)(b / p.poses) * p.rgb_sb;
+    const float *sig_b = p.sigma + (size_t)(b / p.poses) * p.sig_sb;
     const float *obj_b = HAS_OBJ ? p.obj + (size_t)b * p.obj_sb : nullptr;
 
     TgtAcc t;
@@ -318,16 +318,16 @@ static bool make_render_maps(const RenderParams &p, uint32_t bw, uint32_t bh, ui
     const uint64_t w4 = (uint64_t)W * 4, hw4 = (uint64_t)H * W * 4;
     {
         // a batch stride of 0 (one MPI under several poses) is a batch extent of 1; the kernels then ask for entry 0
-        const bool one = B == 1 || p.rgb_sb == 0;
-        const uint64_t d[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)S, (uint64_t)(one ? 1 : B)};
+        const bool one = B == p.poses || p.rgb_sb == 0;
+        const uint64_t d[5] = {(uint64_t)W, (uint64_t)H, 3, (uint64_t)S, (uint64_t)(one ? 1 : B / p.poses)};
         const uint64_t sb[4] = {w4, (uint64_t)p.rgb_sc * 4, (uint64_t)(S > 1 ? p.rgb_ss : p.rgb_sc * 3) * 4,
                                 (uint64_t)(one ? (int64_t)hw4 : p.rgb_sb * 4)};
         if (p.rgb_sc <= 0 || p.rgb_ss < 0 || p.rgb_sb < 0) return false;
         if (!make_map(&m->rgb, p.rgb, 5, d, sb, bw, bh, 3)) return false;
     }
     {
-        const bool one = B == 1 || p.sig_sb == 0;
-        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)S, (uint64_t)(one ? 1 : B)};
+        const bool one = B == p.poses || p.sig_sb == 0;
+        const uint64_t d[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)S, (uint64_t)(one ? 1 : B / p.poses)};
         const uint64_t sb[3] = {w4, (uint64_t)(S > 1 ? p.sig_ss * 4 : (int64_t)hw4), (uint64_t)(one ? (int64_t)hw4 : p.sig_sb * 4)};
         if (p.sig_ss < 0 || p.sig_sb < 0) return false;
         if (!make_map(&m->sig, p.sigma, 4, d, sb, bw, bh, 1)) return false;
@@ -463,7 +463,10 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     MF_CHECK_ARG(rgb && sigma && disparity && G && Kinv && Kt && workspace);
     MF_CHECK_ARG(out_rgb && out_depth && out_mask && out_flow);
     MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0 && B <= 65535 && (int64_t)H * W < (1ll << 31));
-    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW)) == 0);
+    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW | 0xff00u)) == 0);
+    const int poses = (int)((flags >> 8) & 0xffu) + 1;
+    MF_CHECK_ARG(B % poses == 0);
+    flags &= ~0xff00u;
     MF_CHECK_ARG(((uintptr_t)workspace & 15) == 0);
     if (workspace_bytes < mpiflow_render_workspace_bytes(B, S)) return MPIFLOW_E_WORKSPACE;
     const size_t smem = (size_t)S * sizeof(PlaneConst);
@@ -502,7 +505,7 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     p.sigma = sigma; p.sig_sb = sig_sb; p.sig_ss = sig_ss;
     p.obj = obj; p.obj_sb = obj_sb; p.obj_ss = obj_ss;
     p.pc = pc; p.bc = bc;
-    p.B = B; p.S = S; p.H = H; p.W = W; p.flags = flags;
+    p.B = B; p.S = S; p.H = H; p.W = W; p.flags = flags; p.poses = poses;
     p.out_rgb = out_rgb; p.out_depth = out_depth; p.out_mask = out_mask; p.out_flow = out_flow;
     p.out_obj = out_obj;
     p.spacing_table = table;

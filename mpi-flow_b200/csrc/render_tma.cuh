@@ -27,6 +27,7 @@ struct RenderParams {
     unsigned flags;
     float *out_rgb, *out_depth, *out_mask, *out_flow, *out_obj;
     const float *spacing_table;  // [S,H,W] source-frame plane spacing of batch entry 0, or nullptr (render_pk.cuh)
+    int poses;                   // consecutive frames per MPI (MPIFLOW_POSES_PER_MPI), >= 1
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -211,10 +212,10 @@ render_fused_tma_kernel(const __grid_constant__ CUtensorMap map_rgb, const __gri
         const uint32_t box_bytes = mt.z ? (HAS_OBJ ? 5 : 4) * CH * (uint32_t)sizeof(float) : 0u;
         mbar_arrive_expect_tx(&full[st], box_bytes + Cfg::DIRECT_FLOATS * (uint32_t)sizeof(float));
         // the tile's own (un-warped) sigma for the source-frame weights, mpi_rendering.py:104-120
-        tma_load_4d(dst + 5 * CH, &map_sigd, &full[st], tx0, ty0, sl, p.sig_sb ? b : 0);
+        tma_load_4d(dst + 5 * CH, &map_sigd, &full[st], tx0, ty0, sl, p.sig_sb ? b / p.poses : 0);
         if (mt.z) {
-            tma_load_5d(dst, &map_rgb, &full[st], mt.x, mt.y, 0, sl, p.rgb_sb ? b : 0);
-            tma_load_4d(dst + 3 * CH, &map_sig, &full[st], mt.x, mt.y, sl, p.sig_sb ? b : 0);
+            tma_load_5d(dst, &map_rgb, &full[st], mt.x, mt.y, 0, sl, p.rgb_sb ? b / p.poses : 0);
+            tma_load_4d(dst + 3 * CH, &map_sig, &full[st], mt.x, mt.y, sl, p.sig_sb ? b / p.poses : 0);
             if (HAS_OBJ) tma_load_4d(dst + 4 * CH, &map_obj, &full[st], mt.x, mt.y, p.obj_ss ? sl : 0, p.obj_sb ? b : 0);
         }
     };

@@ -182,22 +182,29 @@ def _fusable(mpi_disparity_src, xyz_tgt, xyz_src, G_tgt_src, K_src_inv):
 
 
 def render_fused(mpi_rgb_src, mpi_sigma_src, mpi_disparity_src, G_tgt_src, K_src_inv, K_tgt, obj_mask=None,
-                 is_bg_depth_inf=False, hard_flow=False, out=None):
+                 is_bg_depth_inf=False, hard_flow=False, out=None, poses_per_mpi=1):
     """The fused kernel on its own inputs: rgb BxSx3xHxW, sigma BxSx1xHxW (views are fine), disparity
     BxS, G Bx4x4, K_src_inv/K_tgt Bx3x3, obj_mask BxSx1xHxW or anything expandable to it.
+    poses_per_mpi = P > 1: rgb / sigma hold B/P MPIs, frames b*P .. b*P+P-1 render MPI b (everything else is per frame).
 
     -> (rgb Bx3xHxW, depth Bx1xHxW, mask Bx1xHxW, flowA2B Bx2xHxW, obj Bx1xHxW or None), fp32."""
     B, S, _, H, W = mpi_rgb_src.shape
+    if not 1 <= poses_per_mpi <= 256:
+        raise ValueError("poses_per_mpi must be in 1..256")
+    B *= poses_per_mpi
     rgb, sig = nat.dev(mpi_rgb_src, "mpi_rgb_src"), nat.dev(mpi_sigma_src, "mpi_sigma_src")
     if not nat.inner_contiguous(rgb):
         rgb = rgb.contiguous()
     if not nat.inner_contiguous(sig):
         sig = sig.contiguous()
     device = rgb.device
+    # per-MPI arguments are repeated for the poses of each MPI; per-frame arguments pass through
+    per_frame = lambda t: t.repeat_interleave(poses_per_mpi, 0) if (poses_per_mpi > 1 and t.shape[0] * poses_per_mpi == B) else t
     G = G_tgt_src if G_tgt_src.dim() == 3 else G_tgt_src.unsqueeze(0)
-    G = _dense(G.to(device).expand(B, 4, 4), "G_tgt_src")
-    disp = _dense(mpi_disparity_src.to(device), "mpi_disparity_src")
-    kinv, kt = _dense(K_src_inv.to(device), "K_src_inv"), _dense(K_tgt.to(device), "K_tgt")
+    G = _dense(per_frame(G.to(device)).expand(B, 4, 4), "G_tgt_src")
+    disp = _dense(per_frame(mpi_disparity_src.to(device)).expand(B, S), "mpi_disparity_src")
+    kinv = _dense(per_frame(K_src_inv.to(device)).expand(B, 3, 3), "K_src_inv")
+    kt = _dense(per_frame(K_tgt.to(device)).expand(B, 3, 3), "K_tgt")
     obj = None
     obj_sb = obj_ss = 0
     if obj_mask is not None:
@@ -219,7 +226,7 @@ def render_fused(mpi_rgb_src, mpi_sigma_src, mpi_disparity_src, G_tgt_src, K_src
     nat.check(L.mpiflow_render_fused_f32(
         nat.ptr(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), nat.ptr(sig), sig.stride(0), sig.stride(1),
         nat.ptr(obj), obj_sb, obj_ss, nat.ptr(disp), nat.ptr(G), nat.ptr(kinv), nat.ptr(kt), B, S, H, W,
-        _flags(is_bg_depth_inf, hard_flow), nat.ptr(o_rgb), nat.ptr(o_depth), nat.ptr(o_mask), nat.ptr(o_flow),
+        _flags(is_bg_depth_inf, hard_flow) | ((poses_per_mpi - 1) << 8), nat.ptr(o_rgb), nat.ptr(o_depth), nat.ptr(o_mask), nat.ptr(o_flow),
         nat.ptr(o_obj), nat.ptr(ws), ws_bytes, nat.ptr(status), nat.stream(rgb)))
     if CHECK_SINGULAR and int(status.item()):
         raise Exception("Matrix inverse contains nan!")

@@ -134,6 +134,34 @@ def render_sample_pair(src_imgs, obj_mask, mpi_all_src, disparity_all_src, k_src
     return flow_mix, frame_mix, fill_mask, (rgb2, obj2, flow2)
 
 
+def render_sample_pairs(src_imgs, obj_masks, mpi_all_src, disparity_all_src, k_src_inv, k_tgt, poses, hard_flow=False,
+                        mask_thresh=0.99):
+    """N samples per launch (dataset-scale use; the reference has no batched form): src_imgs Nx3xHxW, obj_masks
+    Nx1xHxW, mpi_all_src NxSx4xHxW, disparity NxS, k_src_inv / k_tgt Nx3x3, poses Nx2x4x4 (object pose, camera pose).
+    One blend launch, ONE render launch of 2N frames (MPIFLOW_POSES_PER_MPI(2): each MPI is read for both of its
+    poses), N merge launches.  -> flow_mix NxHxWx2 f32, frame_mix NxHxWx3 u8 BGR, fill_mask NxHxW u8 (device)."""
+    N, S, _, H, W = mpi_all_src.shape
+    device = mpi_all_src.device
+    mpi_rgb, mpi_sigma = mpi_all_src[:, :, 0:3], mpi_all_src[:, :, 3:]
+    blended = blend_src_into_mpi(src_imgs, mpi_rgb, mpi_sigma, disparity_all_src, k_src_inv)
+    obj = nat.dev(obj_masks, "obj_masks").reshape(N, 1, H, W).contiguous()
+    masks = torch.stack((obj, 1 - obj), 1).reshape(2 * N, 1, 1, H, W)
+    rgb2, _, _, flow2, obj2 = mpi_rendering.render_fused(
+        blended, nat.dev(mpi_sigma), disparity_all_src, poses.to(device).float().reshape(2 * N, 4, 4), k_src_inv,
+        k_tgt, masks, False, hard_flow, poses_per_mpi=2)
+    flow_mix = torch.empty((N, H, W, 2), dtype=torch.float32, device=device)
+    frame_mix = torch.empty((N, H, W, 3), dtype=torch.uint8, device=device)
+    fill_mask = torch.empty((N, H, W), dtype=torch.uint8, device=device)
+    L, st = nat.lib(), nat.stream(rgb2)
+    for n in range(N):
+        a, b = 2 * n, 2 * n + 1
+        nat.check(L.mpiflow_assemble_sample_f32(
+            nat.ptr(rgb2[a]), nat.ptr(rgb2[b]), nat.ptr(obj2[a]), nat.ptr(obj2[b]), nat.ptr(flow2[a]), nat.ptr(flow2[b]),
+            nat.ptr(obj[n]), float(mask_thresh), H, W, nat.ptr(flow_mix[n]), nat.ptr(frame_mix[n]),
+            nat.ptr(fill_mask[n]), st))
+    return flow_mix, frame_mix, fill_mask
+
+
 def render_3dphoto_dynamic(opt, src_imgs, obj_mask, disp, mpi_all_src, disparity_all_src, k_src, k_tgt,
                            data_path=None, name=None, hard_flow=False, mask_thresh=0.99):
     """One training pair from one MPI: -> (flow_mix HxWx2 f32, src_np HxWx3 u8 BGR, inpainted HxWx3 u8 BGR, None);

@@ -196,3 +196,62 @@ def test_render_3dphoto_dynamic_end_to_end(gold):
     np.testing.assert_allclose(flow_mix, gold["flow_mix"], rtol=0, atol=1e-3)
     keep = gold["fill_mask"] == 0
     assert (np.abs(inpainted.astype(np.int16) - gold["inpainted"].astype(np.int16))[keep] <= 1).mean() > 0.99
+
+
+@pytest.mark.gpu
+def test_poses_per_mpi_equals_materialised_batch():
+    """MPIFLOW_POSES_PER_MPI(P): frames b*P..b*P+P-1 read MPI b == the same launch on repeat_interleave'd MPIs"""
+    import _native as nat
+    import synth
+    from utils.mpi import mpi_rendering as R
+    for (S, H, W, N, P) in ((6, 40, 64, 2, 2), (5, 70, 200, 2, 3), (64, 384, 1280, 2, 2), (7, 48, 128, 4, 2)):
+        inp = synth.frame_inputs(N * P, S, H, W, "white", "random", 114532)
+        mpi = T(inp["mpi"][:N]).cuda()
+        G, Kinv, K, disp = (T(inp[k]).cuda() for k in ("G", "Kinv", "K", "disparity"))
+        obj = T(inp["obj_mask"]).cuda().reshape(N * P, 1, 1, H, W)
+        a = R.render_fused(mpi[:, :, :3], mpi[:, :, 3:], disp[:N], G, Kinv[:N], K[:N], obj, poses_per_mpi=P)
+        rep = mpi.repeat_interleave(P, 0)
+        b = R.render_fused(rep[:, :, :3], rep[:, :, 3:], disp, G, Kinv, K, obj)
+        for x, y in zip(a, b):
+            assert x.shape[0] == N * P and torch.equal(x, y), (S, H, W, N, P)
+    with pytest.raises(nat.MpiflowError):        # 3 frames cannot be pairs: MPIFLOW_E_BADARG before any launch
+        _OddFrames.outs(3, 40, 64)
+
+
+class _OddFrames:
+    """render_fused with a frame count that is not a multiple of the poses: drive the C entry directly"""
+
+    @staticmethod
+    def outs(B, H, W):
+        import _native as nat
+        new = lambda c: torch.empty((B, c, H, W), device="cuda")
+        o = (new(3), new(1), new(1), new(2), None)
+        ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+        z = torch.zeros(64, 16, device="cuda")
+        nat.check(nat.lib().mpiflow_render_fused_f32(
+            nat.ptr(z), 1, 1, 1, nat.ptr(z), 1, 1, None, 0, 0, nat.ptr(z), nat.ptr(z), nat.ptr(z), nat.ptr(z),
+            B, 2, H, W, (2 - 1) << 8, nat.ptr(o[0]), nat.ptr(o[1]), nat.ptr(o[2]), nat.ptr(o[3]), None, nat.ptr(ws),
+            1 << 20, None, None))
+        return o
+
+
+@pytest.mark.gpu
+def test_batched_sample_pairs_equal_single_samples(gold):
+    from utils import utils as U
+    mpi, src, obj, disp, K, G_obj, G_cam = _dev(gold, "in_mpi", "in_src", "in_obj", "in_disparity", "in_K", "G_obj",
+                                                "G_cam")
+    kinv = _kinv(gold).cuda()
+    N = 3
+    mpis = torch.cat([mpi * (1 - 0.1 * n) for n in range(N)], 0)                  # three different MPIs
+    poses = torch.stack([torch.stack((G_obj, G_cam)), torch.stack((G_cam, G_obj)), torch.stack((G_obj, G_obj))], 0)
+    rep = lambda t: t.expand(N, *t.shape[1:]).contiguous()
+    flow_b, frame_b, fill_b = U.render_sample_pairs(rep(src), rep(obj.reshape(1, 1, *obj.shape[-2:])), mpis, rep(disp),
+                                                    rep(kinv), rep(K), poses)
+    for n in range(N):
+        flow_1, frame_1, fill_1, _ = U.render_sample_pair(src, obj, mpis[n:n + 1], disp, K, K, poses[n, 0], poses[n, 1],
+                                                          k_src_inv=kinv)
+        np.testing.assert_allclose(flow_b[n].cpu().numpy(), flow_1.cpu().numpy(), rtol=0, atol=5e-6)
+        assert (fill_b[n] != fill_1).float().mean().item() < 0.002
+        assert (frame_b[n] != frame_1).float().mean().item() < 0.005
+    # sample 0 is the fixture's sample
+    np.testing.assert_allclose(flow_b[0].cpu().numpy(), gold["flow_mix"], rtol=0, atol=1e-4)

@@ -74,6 +74,26 @@ def main():
         return U.render_sample_pair(s.src, s.obj, s.mpi2[:1], s.disp, s.K, s.K, s.G[0], s.G[1], k_src_inv=s.Kinv)
     out["sample_us"] = timed(sample, steps)
     out["samples_per_s"] = 1e6 / out["sample_us"]
+
+    # N samples per launch (MPIFLOW_POSES_PER_MPI(2)): 2N frames in one render launch
+    N = int(os.environ.get("SAMPLES_PER_LAUNCH", 8))
+    s = samples[0]
+    batches = []
+    for k in range(2):
+        gen = torch.Generator(device="cuda").manual_seed(k)
+        mpis = torch.rand((N, S, 4, H, W), device="cuda", generator=gen)
+        mpis[:, :, 3].sub_(0.5).clamp_(min=0).add_(1e-4)
+        pose_idx = torch.randint(0, 2, (N, 2), generator=torch.Generator().manual_seed(k))
+        batches.append(types.SimpleNamespace(
+            mpis=mpis, src=torch.rand((N, 3, H, W), device="cuda", generator=gen), obj=s.obj.expand(N, 1, H, W).contiguous(),
+            disp=s.disp.expand(N, S).contiguous(), Kinv=s.Kinv.expand(N, 3, 3).contiguous(),
+            K=s.K.expand(N, 3, 3).contiguous(), poses=s.G[pose_idx.reshape(-1)].reshape(N, 2, 4, 4).contiguous()))
+
+    def batch(i):
+        b = batches[i % 2]
+        return U.render_sample_pairs(b.src, b.obj, b.mpis, b.disp, b.Kinv, b.K, b.poses)
+    us = timed(batch, max(4, steps // 4))
+    out["batched"] = {"samples_per_launch": N, "us_per_sample": us / N, "samples_per_s": N * 1e6 / us}
     print(json.dumps(out))
 
 
