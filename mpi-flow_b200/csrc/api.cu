@@ -38,6 +38,8 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
 {
     MF_CHECK_ARG(mpi && disparity && G && Kinv && Kt && out_rgb && out_depth && out_mask && out_flow);
     MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0);
+    // the host path streams one dense MPI per frame: MPIFLOW_POSES_PER_MPI belongs to the device entry point
+    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW)) == 0);
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     cudaError_t e;
     for (int i = 0; i < 2; i++)

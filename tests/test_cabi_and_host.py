@@ -43,6 +43,12 @@ def test_argument_errors_do_not_need_a_gpu():
     assert L.mpiflow_forward_warp_workspace_bytes(384, 1280) > 5 * 4 * 384 * 1280
     assert L.mpiflow_homography_flow_f32(None, 1, 4, 4, None, None) == -1
     assert L.mpiflow_forward_warp_host(None, None, None, None, None, 0, 5) == 0  # empty image: no-op
+    z = np.zeros(64, np.float32)
+    zp = ctypes.c_void_p(z.ctypes.data)
+    # MPIFLOW_POSES_PER_MPI is a device-entry flag: the host entry rejects it before touching the device
+    assert L.mpiflow_render_fused_host(zp, None, zp, zp, zp, zp, 2, 1, 2, 4, (2 - 1) << 8, zp, zp, zp, zp, None) == -1
+    assert L.mpiflow_blend_src_f32(None, 0, 0, 0, None, 0, 0, None, None, None, 1, 1, 2, 4, None, None) == -1
+    assert L.mpiflow_assemble_sample_f32(zp, zp, zp, zp, zp, zp, zp, 0.99, 0, 4, zp, zp, zp, None) == -1
 
 
 def test_python_interface_mirrors_reference_signatures():
