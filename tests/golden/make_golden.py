@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference,
 CPU, fp32) on seeded synthetic inputs.  Run in the build container only:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            [--warpback-only | --flow-io-only | --sample-only | --moving-obj-only]
 
 The reference hard-codes CUDA in two places (utils/mpi/homography_sampler.py:16-17); for a CPU run
 they are shimmed: torch.cuda.synchronize -> no-op, Tensor.cuda -> identity.  Nothing of the
