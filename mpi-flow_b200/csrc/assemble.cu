@@ -6,6 +6,7 @@
 //                          (:253-283) -> flow_mix f32 [H,W,2], frame_mix u8 BGR [H,W,3], fill_mask u8 [H,W]
 // Both are streaming kernels, one thread per pixel; HBM-bound.
 #include "common.cuh"
+#include <cstdlib>
 
 // blend_weights of mpi_rendering.render in the source frame (plane_volume_rendering, mpi_rendering.py:62-99 with
 // xyz = K^-1 (x,y,1) / disparity, :213-239): the exclusive running product of (T + 1e-6), T = exp(-sigma * dist).
@@ -72,9 +73,19 @@ MPIFLOW_API int mpiflow_blend_src_f32(const float *rgb, int64_t rgb_sb, int64_t 
 {
     if (!rgb || !sigma || !src_img || !disparity || !Kinv || !out_rgb) return MPIFLOW_E_BADARG;
     if (B <= 0 || S <= 0 || H <= 0 || W <= 0 || H > 65535 || B > 65535) return MPIFLOW_E_BADARG;
-    dim3 grid((W + 255) / 256, H, B);
-    blend_src_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(rgb, rgb_sb, rgb_ss, rgb_sc, sigma, sig_sb, sig_ss,
-                                                                src_img, disparity, Kinv, S, H, W, out_rgb);
+    static const int unroll = []() {   // MPIFLOW_BLEND_UNROLL=2|4|8: planes loaded ahead per thread (A/B measurements)
+        const char *e = getenv("MPIFLOW_BLEND_UNROLL");
+        return e ? atoi(e) : 4;
+    }();
+    static const int block = []() {
+        const char *e = getenv("MPIFLOW_BLEND_BLOCK");
+        const int v = e ? atoi(e) : 256;
+        return (v == 64 || v == 128 || v == 256) ? v : 256;
+    }();
+    dim3 grid((W + block - 1) / block, H, B);
+    auto kern = unroll == 8 ? blend_src_kernel<8> : unroll == 2 ? blend_src_kernel<2> : blend_src_kernel<4>;
+    kern<<<grid, block, 0, (cudaStream_t)stream>>>(rgb, rgb_sb, rgb_ss, rgb_sc, sigma, sig_sb, sig_ss, src_img, disparity,
+                                                   Kinv, S, H, W, out_rgb);
     return mf_launch_status();
 }
 
