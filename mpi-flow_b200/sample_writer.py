@@ -1,0 +1,112 @@
+"""Asynchronous sample writer -- the step after the path (reference
+gen_3dphoto_dynamic_v2.py:107-122 and utils/utils.py:284-286).
+
+The reference finishes every sample synchronously: device->host copies, cv2.inpaint, writeFlow and two cv2.imwrite
+calls sit between two renders, so the GPU idles while the disk and OpenCV work.  Here submit() only enqueues three
+device->pinned-host copies on a side stream (flow_mix, frame_mix, fill_mask -- 12.3 + 1.5 + 0.5 MB at 1280x384) and
+returns; worker threads wait for the copy event, fill the holes (cv2.inpaint, INPAINT_NS, radius 3, as :284-286) and
+write  flows/<name>.flo, dst_images/<name>.png, src_images/<name>.png  exactly as the reference names them.
+A bounded ring of pinned slots gives back-pressure instead of unbounded host memory.
+"""
+import os
+import queue
+import threading
+
+import numpy as np
+import torch
+
+from write_flow import writeFlow
+
+
+class SampleWriter:
+    def __init__(self, out_dir, workers=2, depth=4):
+        import cv2  # host-side hole filling and PNG encoding
+        self._cv2 = cv2
+        self.out_dir = out_dir
+        for sub in ("flows", "dst_images", "src_images"):
+            os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
+        self._depth = depth
+        self._free = queue.Queue()          # pinned slots, created on first use (shapes are not known before)
+        self._slots_made = 0
+        self._jobs = queue.Queue()
+        self._errors = []
+        self._copy_stream = None
+        self._threads = [threading.Thread(target=self._work, daemon=True) for _ in range(workers)]
+        for t in self._threads:
+            t.start()
+
+    # ------------------------------------------------------------------------------------------------
+    def _slot(self, shapes):
+        """a set of pinned host buffers matching `shapes`; blocks when all `depth` slots are in flight"""
+        while True:
+            if self._slots_made < self._depth and self._free.empty():
+                self._slots_made += 1
+                pin = torch.cuda.is_available()
+                return [torch.empty(s, dtype=d, pin_memory=pin) for s, d in shapes]
+            slot = self._free.get()
+            if [(tuple(t.shape), t.dtype) for t in slot] == shapes:
+                return slot
+            self._slots_made -= 1           # shape changed: drop the old slot, make a new one
+
+    def submit(self, name, flow_mix, frame_mix, fill_mask, src_np):
+        """flow_mix HxWx2 f32, frame_mix HxWx3 u8 (BGR, holes 255), fill_mask HxW u8 (1 = hole): CUDA or CPU tensors /
+        arrays, e.g. the outputs of utils.utils.render_sample_pair; src_np HxWx3 u8 BGR (host).  Returns at once."""
+        if self._errors:
+            raise self._errors[0]
+        tensors = [torch.as_tensor(t) for t in (flow_mix, frame_mix, fill_mask)]
+        shapes = [(tuple(t.shape), t.dtype) for t in tensors]
+        slot = self._slot(shapes)
+        event = None
+        if any(t.is_cuda for t in tensors):
+            dev = next(t.device for t in tensors if t.is_cuda)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream.wait_stream(torch.cuda.current_stream(dev))     # after the kernels that produced them
+            with torch.cuda.stream(self._copy_stream):
+                for h, t in zip(slot, tensors):
+                    h.copy_(t, non_blocking=True)
+                    if t.is_cuda:
+                        t.record_stream(self._copy_stream)
+                event = torch.cuda.Event()
+                event.record(self._copy_stream)
+        else:
+            for h, t in zip(slot, tensors):
+                h.copy_(t)
+        self._jobs.put((name, slot, event, np.ascontiguousarray(src_np)))
+
+    def _work(self):
+        cv2 = self._cv2
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            name, slot, event, src_np = job
+            try:
+                if event is not None:
+                    event.synchronize()
+                flow, frame, fill = (t.numpy() for t in slot)
+                inpainted = cv2.inpaint(frame, fill, 3, cv2.INPAINT_NS)                      # utils/utils.py:284-286
+                writeFlow(os.path.join(self.out_dir, "flows", f"{name}.flo"), flow)           # gen...v2.py:120
+                cv2.imwrite(os.path.join(self.out_dir, "dst_images", f"{name}.png"), inpainted)
+                cv2.imwrite(os.path.join(self.out_dir, "src_images", f"{name}.png"), src_np)
+            except Exception as e:      # surfaced by the next submit() / close()
+                self._errors.append(e)
+            finally:
+                self._free.put(slot)
+                self._jobs.task_done()
+
+    def close(self):
+        """wait for everything submitted, stop the workers, re-raise the first error"""
+        self._jobs.join()
+        for _ in self._threads:
+            self._jobs.put(None)
+        for t in self._threads:
+            t.join()
+        if self._errors:
+            raise self._errors[0]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
