@@ -30,8 +30,17 @@ def main():
     T = lambda a: torch.from_numpy(a).cuda()
     inp = synth.frame_inputs(1, S, H, W, "smooth", "random", 114514)
     mpi = T(inp["mpi"])
-    mpi[:, :, 3] *= 4.0                                   # mostly opaque, like a predicted MPI: few holes to fill
-    obj, disp, K, Kinv = T(inp["obj_mask"]), T(inp["disparity"]), T(inp["K"]), T(inp["Kinv"])
+    # a surface-like scene, as a predicted MPI is: density concentrated around one plane per pixel (a smooth depth
+    # field in the far two thirds of the volume), an opaque last plane, one hard instance mask (gen...v2.py:101);
+    # holes are then the disocclusions around the moved object and at the image border (about 5 % of the pixels)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32, device="cuda"),
+                            torch.arange(W, dtype=torch.float32, device="cuda"), indexing="ij")
+    surface = S * (0.8 + 0.12 * torch.sin(xx / W * 6.0) * torch.cos(yy / H * 4.0))
+    planes = torch.arange(S, dtype=torch.float32, device="cuda").view(1, S, 1, 1)
+    mpi[:, :, 3] = 50 * torch.exp(-0.5 * (planes - surface) ** 2) + 1e-4
+    mpi[:, -1, 3] += 10.0
+    disp, K, Kinv = T(inp["disparity"]), T(inp["K"]), T(inp["Kinv"])
+    obj = ((((xx - 0.4 * W) / (0.18 * W)) ** 2 + ((yy - 0.55 * H) / (0.3 * H)) ** 2) < 1).float()[None, None]
     src = mpi[:, 0, 0:3].contiguous()
     src_np = (src[0].permute(1, 2, 0) * 255).round().clamp(0, 255).to(torch.uint8).flip(-1).contiguous().cpu().numpy()
     random.seed(114514)
