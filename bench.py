@@ -294,7 +294,9 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "frames_per_step_per_gpu": Be, "steps": e2e_steps,
                     "api": "mpiflow_render_fused_host (pinned host buffers)"},
-            "gpu_launches": 3 * args.steps,  # plane_consts + batch_flags + render_fused_pk per step
+            # plane_consts + batch_flags (+ spacing_table when >= 4 frames share K^-1 and disparities) + render_fused_pk
+            # per step (profiles/r01_pk_launches.csv)
+            "gpu_launches": (4 if B >= 4 else 3) * args.steps,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "render_fused_pk_kernel (persistent, warp-specialised; step = prologue + this kernel)",
