@@ -165,8 +165,7 @@ int mpiflow_rasterize_mesh_f32(const float *verts_ndc, const int64_t *faces, con
  * w = blend_weights[b,s] = prod_{j<s} (exp(-sigma_j * dist_j) + 1e-6) in the source frame.  One pass: 4 S channels
  * read, 3 S written, no xyz / weight tensors.
  *   rgb / sigma: strided as in mpiflow_render_fused_f32; src_img [B,3,H,W]; disparity [B,S]; Kinv [B,3,3]
- *   out_rgb [B,S,3,H,W] dense; may be the rgb buffer itself when that is dense (each element is read once, before
- *   its write, by the same thread) */
+ *   out_rgb [B,S,3,H,W] dense, must not overlap the inputs */
 int mpiflow_blend_src_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc, const float *sigma,
                           int64_t sig_sb, int64_t sig_ss, const float *src_img, const float *disparity,
                           const float *Kinv, int B, int S, int H, int W, float *out_rgb, void *stream);
