@@ -59,3 +59,44 @@ def test_two_ranks_gather_in_batch_order(n_frames):
         assert torch.equal(whole[f, 0], torch.full((3, 4), float(f)))
         assert torch.equal(whole[f, 1], torch.full((3, 4), float(f) + 1))
     assert slowest == 2.0
+
+
+def _writer_worker(rank, world, port, n_samples, out_dir, golden):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "mpi-flow_b200")]
+    import numpy as np
+    import shard
+    from sample_writer import SampleWriter
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = np.load(golden)
+        lo, hi = shard.shard_range(n_samples, rank, world)
+        with SampleWriter(out_dir, workers=2, depth=2) as w:      # every rank writes its own samples, no exchange
+            for k in range(lo, hi):
+                w.submit(f"demo_{k}", g["flow_mix"] + np.float32(k), g["frame_mix"], g["fill_mask"], g["src_np"])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_write_disjoint_samples(tmp_path, golden_dir):
+    """dataset generation at N>1: samples are sharded like frames, each rank's writer produces its own files"""
+    pytest.importorskip("cv2")
+    import numpy as np
+    sys.path[:0] = [os.path.join(ROOT, "mpi-flow_b200")]
+    import write_flow
+    golden = os.path.join(golden_dir, "sample_pair.npz")
+    n = 5
+    ctx = mp.get_context("spawn")
+    port = 29500 + (os.getpid() % 400) + 17
+    procs = [ctx.Process(target=_writer_worker, args=(r, 2, port, n, str(tmp_path), golden)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    g = np.load(golden)
+    assert sorted(os.listdir(tmp_path / "flows")) == sorted(f"demo_{k}.flo" for k in range(n))
+    assert sorted(os.listdir(tmp_path / "dst_images")) == sorted(f"demo_{k}.png" for k in range(n))
+    for k in range(n):
+        assert np.array_equal(write_flow.readFlow(str(tmp_path / "flows" / f"demo_{k}.flo")), g["flow_mix"] + np.float32(k))
