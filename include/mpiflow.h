@@ -40,6 +40,9 @@ extern "C" {
 #define MPIFLOW_POSES_PER_MPI(n) ((((unsigned)(n) - 1u) & 0xffu) << 8)
 
 int mpiflow_version(void);
+/* frees the per-device staging buffers and streams of the host-pointer entry points (they are re-created on the next
+ * call); the device-pointer entry points keep no state.  Always returns 0. */
+int mpiflow_shutdown(void);
 /* static string for any code returned by this library */
 const char *mpiflow_error_string(int code);
 
@@ -91,7 +94,11 @@ int mpiflow_debug_packed_f32(const float *a, const float *b, const float *c, int
 
 /* Same computation from HOST buffers (dense layouts: mpi [B,S,4,H,W] = rgb+sigma, obj [B,1,H,W]):
  * H2D of the inputs, the two launches, D2H of the five outputs, all inside the call; returns
- * MPIFLOW_E_SINGULAR like the reference raises.  Frames are pipelined over two streams. */
+ * MPIFLOW_E_SINGULAR like the reference raises.  Frames are pipelined over two streams.
+ * Unlike the device-pointer entry points, the host-pointer ones (this one, mpiflow_forward_warp_host,
+ * forward_warping) KEEP STATE between calls: a device staging buffer and two streams per CUDA device (the device
+ * current at the call), created on first use, guarded by a per-device mutex (concurrent callers on one device are
+ * serialised), released by mpiflow_shutdown().  On an error return no copy is left in flight on the caller's buffers. */
 int mpiflow_render_fused_host(const float *mpi, const float *obj, const float *disparity, const float *G,
                               const float *Kinv, const float *Kt, int B, int S, int H, int W,
                               unsigned flags, float *out_rgb, float *out_depth, float *out_mask,

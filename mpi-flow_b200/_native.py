@@ -22,6 +22,7 @@ _P, _I, _I64, _U, _SZ = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint, _c.c_size_
 
 _SIGNATURES = {
     "mpiflow_version": (_I, []),
+    "mpiflow_shutdown": (_I, []),
     "mpiflow_error_string": (_c.c_char_p, [_I]),
     "mpiflow_plane_homographies_f32": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P]),
     "mpiflow_render_workspace_bytes": (_SZ, [_I, _I]),

@@ -13,9 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpiflow_sm100.so")
 WARPLIB = os.path.join(HERE, "external", "forward_warping", "libwarping.so")
-SOURCES = ["api.cu", "homography.cu", "render_fused.cu", "composite.cu", "splat.cu", "raster.cu", "assemble.cu"]
+SOURCES = ["api.cu", "homography.cu", "render_fused.cu", "render_pk16.cu", "render_pk8.cu", "composite.cu", "splat.cu",
+           "raster.cu", "assemble.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static", "--threads", "0"]
 
 
 def _stale(target, deps):

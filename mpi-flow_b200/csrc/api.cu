@@ -18,15 +18,41 @@ MPIFLOW_API const char *mpiflow_error_string(int code)
 }
 
 namespace {
+// State of the host-buffer entry point: one staging buffer and two copy streams PER DEVICE (the device that is current
+// when the call is made), created on first use, serialised by a per-device mutex, released by mpiflow_shutdown().
+constexpr int MF_MAX_DEVICES = 64;
 struct HostCtx {
     std::mutex mu;
     void *buf = nullptr;
     size_t cap = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
 };
-HostCtx g_ctx;
+HostCtx g_ctx[MF_MAX_DEVICES];
 inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 }  // namespace
+
+void mf_splat_shutdown();   // splat.cu: staging buffers of the host-pointer splat
+
+// Releases everything the host-pointer entry points (mpiflow_render_fused_host, mpiflow_forward_warp_host,
+// forward_warping) keep between calls.  The device-pointer entry points keep nothing.
+MPIFLOW_API int mpiflow_shutdown(void)
+{
+    int prev = 0;
+    const bool have_dev = cudaGetDevice(&prev) == cudaSuccess;
+    for (int d = 0; d < MF_MAX_DEVICES; d++) {
+        HostCtx &c = g_ctx[d];
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (!c.buf && !c.streams[0] && !c.streams[1]) continue;
+        cudaSetDevice(d);
+        for (int i = 0; i < 2; i++)
+            if (c.streams[i]) { cudaStreamSynchronize(c.streams[i]); cudaStreamDestroy(c.streams[i]); c.streams[i] = nullptr; }
+        if (c.buf) cudaFree(c.buf);
+        c.buf = nullptr; c.cap = 0;
+    }
+    mf_splat_shutdown();
+    if (have_dev) cudaSetDevice(prev);
+    return 0;
+}
 
 // Host-buffer variant of mpiflow_render_fused_f32: frames are double-buffered over two streams so
 // the H2D of frame b+1 overlaps the kernels and D2H of frame b (pinned host memory gets full PCIe
@@ -40,10 +66,14 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
     MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0);
     // the host path streams one dense MPI per frame: MPIFLOW_POSES_PER_MPI belongs to the device entry point
     MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW)) == 0);
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    cudaError_t e;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e == cudaErrorNoDevice ? MPIFLOW_E_NODEVICE : (int)e;
+    MF_CHECK_ARG(dev >= 0 && dev < MF_MAX_DEVICES);
+    HostCtx &ctx = g_ctx[dev];
+    std::lock_guard<std::mutex> lock(ctx.mu);
     for (int i = 0; i < 2; i++)
-        if (!g_ctx.streams[i] && (e = cudaStreamCreateWithFlags(&g_ctx.streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+        if (!ctx.streams[i] && (e = cudaStreamCreateWithFlags(&ctx.streams[i], cudaStreamNonBlocking)) != cudaSuccess)
             return e == cudaErrorNoDevice ? MPIFLOW_E_NODEVICE : (int)e;
 
     const size_t HW = (size_t)H * W;
@@ -51,18 +81,26 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
     const size_t b_small = al256((S + 16 + 9 + 9) * sizeof(float)), b_out = al256(HW * 8 * sizeof(float));
     const size_t b_ws = al256(mpiflow_render_workspace_bytes(1, S));
     const size_t slot = b_mpi + b_obj + b_small + b_out + b_ws;
-    const size_t need = 2 * slot + al256((size_t)B * sizeof(int));
-    if (need > g_ctx.cap) {
-        if (g_ctx.buf) cudaFree(g_ctx.buf);
-        g_ctx.buf = nullptr; g_ctx.cap = 0;
-        if ((e = cudaMalloc(&g_ctx.buf, need)) != cudaSuccess) return (int)e;
-        g_ctx.cap = need;
+    const size_t need = 2 * slot + al256(2 * sizeof(int));
+    if (need > ctx.cap) {
+        for (int i = 0; i < 2; i++) cudaStreamSynchronize(ctx.streams[i]);
+        if (ctx.buf) cudaFree(ctx.buf);
+        ctx.buf = nullptr; ctx.cap = 0;
+        if ((e = cudaMalloc(&ctx.buf, need)) != cudaSuccess) return (int)e;
+        ctx.cap = need;
     }
-    char *base = reinterpret_cast<char *>(g_ctx.buf);
-    int *d_status = reinterpret_cast<int *>(base + 2 * slot);
+    char *base = reinterpret_cast<char *>(ctx.buf);
+    int *d_status = reinterpret_cast<int *>(base + 2 * slot);   // one flag per stream, sticky over the frames
+    // an early return must not leave copies in flight on the caller's buffers
+    auto fail = [&](int rc) {
+        for (int i = 0; i < 2; i++) cudaStreamSynchronize(ctx.streams[i]);
+        return rc;
+    };
+    if ((e = cudaMemsetAsync(d_status, 0, 2 * sizeof(int), ctx.streams[0])) != cudaSuccess) return (int)e;
+    if ((e = cudaStreamSynchronize(ctx.streams[0])) != cudaSuccess) return (int)e;
 
     for (int b = 0; b < B; b++) {
-        cudaStream_t st = g_ctx.streams[b & 1];
+        cudaStream_t st = ctx.streams[b & 1];
         char *d = base + (size_t)(b & 1) * slot;
         float *d_mpi = (float *)d, *d_obj = (float *)(d + b_mpi);
         float *d_small = (float *)(d + b_mpi + b_obj);
@@ -70,7 +108,7 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
         float *d_out = (float *)(d + b_mpi + b_obj + b_small);
         void *d_ws = d + b_mpi + b_obj + b_small + b_out;
         if ((e = cudaMemcpyAsync(d_mpi, mpi + (size_t)b * S * 4 * HW, HW * 4 * S * sizeof(float),
-                                 cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+                                 cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail((int)e);
         if (obj) cudaMemcpyAsync(d_obj, obj + (size_t)b * HW, HW * sizeof(float), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_disp, disparity + (size_t)b * S, S * sizeof(float), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_G, G + (size_t)b * 16, 16 * sizeof(float), cudaMemcpyHostToDevice, st);
@@ -78,12 +116,14 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
         cudaMemcpyAsync(d_Kt, Kt + (size_t)b * 9, 9 * sizeof(float), cudaMemcpyHostToDevice, st);
         float *o_rgb = d_out, *o_depth = d_out + 3 * HW, *o_mask = d_out + 4 * HW, *o_flow = d_out + 5 * HW,
               *o_obj = d_out + 7 * HW;
-        const int rc = mpiflow_render_fused_f32(
+        // status = nullptr: the prologue kernel only ever raises the flag it is given, so the per-stream flag set
+        // once above collects every frame of that stream
+        const int rc = mf_render_fused_impl(
             d_mpi, (int64_t)S * 4 * HW, (int64_t)4 * HW, (int64_t)HW, d_mpi + 3 * HW, (int64_t)S * 4 * HW,
             (int64_t)4 * HW, obj ? d_obj : nullptr, (int64_t)HW, 0, d_disp, d_G, d_Kinv, d_Kt, 1, S, H, W,
             flags, o_rgb, o_depth, o_mask, o_flow, (obj && out_obj) ? o_obj : nullptr, d_ws, b_ws,
-            d_status + b, st);
-        if (rc) return rc;
+            d_status + (b & 1), /*clear_status=*/false, st);
+        if (rc) return fail(rc);
         cudaMemcpyAsync(out_rgb + (size_t)b * 3 * HW, o_rgb, 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(out_depth + (size_t)b * HW, o_depth, HW * sizeof(float), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(out_mask + (size_t)b * HW, o_mask, HW * sizeof(float), cudaMemcpyDeviceToHost, st);
@@ -92,13 +132,9 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
             cudaMemcpyAsync(out_obj + (size_t)b * HW, o_obj, HW * sizeof(float), cudaMemcpyDeviceToHost, st);
     }
     for (int i = 0; i < 2; i++)
-        if ((e = cudaStreamSynchronize(g_ctx.streams[i])) != cudaSuccess) return (int)e;
-    // error behaviour of homography_sampler.inverse (:24-26): raise when an inverse is NaN
-    int bad = 0;
-    for (int b = 0; b < B && !bad; b++) {
-        int v = 0;
-        if ((e = cudaMemcpy(&v, d_status + b, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return (int)e;
-        bad |= v;
-    }
-    return bad ? MPIFLOW_E_SINGULAR : 0;
+        if ((e = cudaStreamSynchronize(ctx.streams[i])) != cudaSuccess) return fail((int)e);
+    // error behaviour of homography_sampler.inverse (:24-26): raise when an inverse is NaN -- one readback
+    int bad[2] = {0, 0};
+    if ((e = cudaMemcpy(bad, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return (int)e;
+    return (bad[0] | bad[1]) ? MPIFLOW_E_SINGULAR : 0;
 }

@@ -15,7 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "render_pk.cuh"
+#include "render_launch.cuh"
 
 // prologue: PlaneConst for every (b, s); inputs are per batch.
 __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__restrict__ Kinv,
@@ -32,7 +32,9 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
     for (int i = 0; i < 9; i++) { ki[i] = Kinv[(size_t)b * 9 + i]; kt[i] = Kt[(size_t)b * 9 + i]; }
     const float depth = __frcp_rn(disparity[n]);  // torch.reciprocal (mpi_rendering.py:278)
     PlaneConst c;
-    const bool ok = plane_homography(g, ki, kt, depth, c.hts, c.hst);
+    float hts[9];
+    const bool ok = plane_homography(g, ki, kt, depth, hts, c.hst);
+    for (int i = 0; i < 3; i++) { c.g2[i] = hts[i * 3 + 2]; c.g01[2 * i] = hts[i * 3]; c.g01[2 * i + 1] = hts[i * 3 + 1]; }
     // xyz_tgt(ix,iy) = G . [ (Kinv (ix,iy,1)) * depth ; 1 ]  ==  (depth * R Kinv) (ix,iy,1) + t
     // (mpi_rendering.py:213-256, rendering_utils.py:4-23; affine in the pixel position, so the
     //  reference's bilinear sample of the xyz tensor equals this evaluated at the clamped index)
@@ -42,11 +44,17 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
     mm33_fma(R, ki, M);
     for (int i = 0; i < 9; i++) c.P[i] = __fmul_rn(M[i], depth);
     for (int i = 0; i < 3; i++) c.P[i * 3 + 2] = __fadd_rn(c.P[i * 3 + 2], g[i * 4 + 3]);
+    const bool last = s + 1 == S;
+    const float depth_next = last ? depth : __frcp_rn(disparity[n + 1]);
+    // (R^T t)_z: the target ray of pixel q meets plane s at Z = (depth_s + a) / (R^T Kt^-1 q)_z
+    const float a = fmaf(g[2 * 4 + 2], g[2 * 4 + 3], fmaf(g[1 * 4 + 2], g[1 * 4 + 3], g[0 * 4 + 2] * g[0 * 4 + 3]));
     c.depth = depth;
-    c.ddepth = (s + 1 < S) ? __fsub_rn(__frcp_rn(disparity[n + 1]), depth) : 0.f;
-    c.ddepth_l2e = c.ddepth * 1.4426950408889634f;
-    c.depth_next = (s + 1 < S) ? __frcp_rn(disparity[n + 1]) : depth;
-    c.pad = 0.f;
+    c.depth_next = depth_next;
+    c.zc = depth + a;
+    // thickness of the plane along a ray of unit parameter, times log2(e): exp(-sigma*dist) is evaluated as
+    // ex2(-sigma*dist*log2e) in the target frame; the last plane is 1e3 thick (mpi_rendering.py:73-78)
+    c.nmul = last ? 0.f : __fsub_rn(depth_next, depth) * 1.4426950408889634f;
+    c.nadd = last ? 1e3f * 1.4426950408889634f : 0.f;
     pc[n] = c;
     bool okb = true;
     if (s == 0) {
@@ -56,7 +64,7 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
         okb = inverse33_f64(k64, ki64);
         for (int i = 0; i < 9; i++) bc.ktinv[i] = okb ? (float)ki64[i] : 0.f;
         for (int i = 0; i < 3; i++) bc.rt2[i] = g[i * 4 + 2];
-        bc.a = fmaf(g[2 * 4 + 2], g[2 * 4 + 3], fmaf(g[1 * 4 + 2], g[1 * 4 + 3], g[0 * 4 + 2] * g[0 * 4 + 3]));
+        bc.a = a;
         float mind = depth;
         for (int i = 1; i < S; i++) mind = fminf(mind, __frcp_rn(disparity[n + i]));
         bc.min_zc = mind + bc.a;   // NaN-propagating on purpose: a NaN disparity disables the lean loop
@@ -77,8 +85,7 @@ __global__ void batch_flags_kernel(const PlaneConst *__restrict__ pc, BatchConst
     const PlaneConst *p0 = pc + (size_t)b * S;
     bool same = true, shared = have_table != 0;
     for (int s = lane; s < S; s += 32) {
-        for (int i = 0; i < 9; i++)
-            if (i % 3 != 2) same = same && (__float_as_uint(p0[s].hts[i]) == __float_as_uint(p0[0].hts[i]));
+        for (int i = 0; i < 6; i++) same = same && (__float_as_uint(p0[s].g01[i]) == __float_as_uint(p0[0].g01[i]));
         // source-frame plane spacing depends on K_src^-1 and the plane depths only: the table of entry 0 serves entry b
         shared = shared && (__float_as_uint(p0[s].depth) == __float_as_uint(pc[s].depth)) &&
                  (__float_as_uint(p0[s].depth_next) == __float_as_uint(pc[s].depth_next));
@@ -215,9 +222,9 @@ render_fused_kernel(const RenderParams p)
         pr = cr; pg = cg; pb = cb; psig = sg; pm = m; px = X; py = Y; pz = Z;
 
         // ---------------- source frame ----------------
-        const float U = mf_dot3(c.hts[0], c.hts[1], c.hts[2], xf, yf);
-        const float V = mf_dot3(c.hts[3], c.hts[4], c.hts[5], xf, yf);
-        const float Q = mf_dot3(c.hts[6], c.hts[7], c.hts[8], xf, yf);
+        const float U = mf_dot3(c.g01[0], c.g01[1], c.g2[0], xf, yf);
+        const float V = mf_dot3(c.g01[2], c.g01[3], c.g2[1], xf, yf);
+        const float Q = mf_dot3(c.g01[4], c.g01[5], c.g2[2], xf, yf);
         float tu, tv;
         mf_div2(U, V, Q, tu, tv);
         const float du = __fsub_rn(tu, xf), dv = __fsub_rn(tv, yf);  // :212-218
@@ -257,7 +264,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 MPIFLOW_API size_t mpiflow_render_workspace_bytes(int B, int S)
 {
     if (B <= 0 || S <= 0) return 0;
-    return align_up((size_t)B * S * sizeof(PlaneConst), 256) + align_up((size_t)B * sizeof(BatchConst), 256) + 256;
+    // one record more than B*S: the persistent kernel copies S + 1 records per tile (render_pk.cuh)
+    return align_up(((size_t)B * S + 1) * sizeof(PlaneConst), 256) + align_up((size_t)B * sizeof(BatchConst), 256) + 256;
 }
 
 // the same plus room for the [S,H,W] plane-spacing table (see spacing_table_kernel): a launch that gets this much
@@ -305,13 +313,9 @@ static bool make_map(CUtensorMap *m, const float *ptr, int rank, const uint64_t 
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct RenderMaps {
-    CUtensorMap rgb, sig, obj, sigd, dist;
-};
-
 // tensor maps over the caller's planar tensors: rgb (W,H,3,S,B) box (bw,bh,3), sigma / mask (W,H,S,B) box
 // (bw,bh), and sigma again with the tile itself as the box (un-warped sigma of the source-frame weights)
-static bool make_render_maps(const RenderParams &p, uint32_t bw, uint32_t bh, uint32_t tw, uint32_t th, RenderMaps *m)
+bool mf_make_render_maps(const RenderParams &p, uint32_t bw, uint32_t bh, uint32_t tw, uint32_t th, RenderMaps *m)
 {
     const int B = p.B, S = p.S, H = p.H, W = p.W;
     if ((W % 4) != 0) return false;
@@ -352,74 +356,22 @@ static bool make_render_maps(const RenderParams &p, uint32_t bw, uint32_t bh, ui
     return true;
 }
 
-template <class Cfg>
-static int launch_tma(const RenderParams &p, cudaStream_t st, bool *used)
+int mf_sm_count()
 {
-    *used = false;
-    const size_t smem = Cfg::smem_bytes(p.S);
-    if (smem > 227 * 1024) return 0;
-    RenderMaps m;
-    if (!make_render_maps(p, Cfg::BW, Cfg::BH, Cfg::TW, Cfg::TH, &m)) return 0;
-    const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
-    auto kern = p.obj ? (hard ? render_fused_tma_kernel<Cfg, true, true> : render_fused_tma_kernel<Cfg, true, false>)
-                      : (hard ? render_fused_tma_kernel<Cfg, false, true> : render_fused_tma_kernel<Cfg, false, false>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    dim3 grid((p.W + Cfg::TW - 1) / Cfg::TW, (p.H + Cfg::TH - 1) / Cfg::TH, p.B);
-    kern<<<grid, Cfg::THREADS, smem, st>>>(m.rgb, m.sig, m.obj, m.sigd, p);
-    *used = true;
-    return mf_launch_status();
+    // per device: a process may render on several GPUs
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev];
+    if (v > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    cached[dev] = v;
+    return v;
 }
 
-static int sm_count()
-{
-    static const int n = []() {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-        return v;
-    }();
-    return n;
-}
-
-// persistent packed-fp32 renderer (render_pk.cuh): one CTA per SM, tiles from the counter the prologue reset
-template <class Cfg>
-static int launch_pk(const RenderParams &p, int *tile_counter, cudaStream_t st, bool *used)
-{
-    *used = false;
-    const size_t smem = Cfg::smem_bytes(p.S);
-    if (smem > 227 * 1024) return 0;
-    RenderMaps m;
-    if (!make_render_maps(p, Cfg::BW, Cfg::BH, Cfg::TW, Cfg::TH, &m)) return 0;
-    const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
-    auto kern = p.obj ? (hard ? render_fused_pk_kernel<Cfg, true, true> : render_fused_pk_kernel<Cfg, true, false>)
-                      : (hard ? render_fused_pk_kernel<Cfg, false, true> : render_fused_pk_kernel<Cfg, false, false>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const long long ntiles = (long long)((p.W + Cfg::TW - 1) / Cfg::TW) * ((p.H + Cfg::TH - 1) / Cfg::TH) * p.B;
-    const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-    kern<<<grid, Cfg::THREADS, smem, st>>>(m.rgb, m.sig, m.obj, m.sigd, m.dist, p, tile_counter);
-    *used = true;
-    return mf_launch_status();
-}
-
-// tile 64x8, box 80x16, 3-stage ring, 2 pixels per thread, 8 warps, 2 CTAs / SM (independent rings
-// fill each other's barrier waits): 83 KB of stages + 8 KB of plane constants per CTA
-typedef TmaCfg<64, 8, 80, 16, 3, 2, 2> CfgDefault;
-// experimental shapes, selected with MPIFLOW_TMA_CFG=1..3 (A/B measurements only)
-typedef TmaCfg<64, 16, 80, 24, 4, 2> CfgFull;        // 64x16 tiles, 16 warps, 1 CTA / SM
-typedef TmaCfg<32, 16, 48, 24, 4, 2, 2> CfgNarrow;  // 32x16 tiles, 2 CTAs / SM
-typedef TmaCfg<64, 16, 80, 24, 3, 2> CfgShallow;    // 3-stage ring
-
-// persistent kernel: tile 64x16, box 80x20 (zoom up to ~1.19), 5-stage ring, one pixel pair per thread, 16+2 warps
-typedef PkCfg<64, 16, 80, 20, 5, 1> PkDefault;
-// A/B shapes, selected with MPIFLOW_PK_CFG
-typedef PkCfg<64, 16, 80, 20, 5, 2> PkTwoPairs;  // 8+2 warps, two pairs per thread
-typedef PkCfg<64, 8, 80, 12, 8, 1> PkSmallTile;  // 64x8 tiles, 8+2 warps: small launches (few tiles per SM)
-typedef PkCfg<64, 16, 96, 20, 5, 1> PkWideBox;   // row pitch = 0 mod 32 banks: rows of a footprint never collide
-typedef PkCfg<64, 16, 72, 20, 6, 1> PkNarrowBox; // less overfetch, deeper ring
-typedef PkCfg<64, 24, 80, 28, 3, 2> Pk24x2;      // 12+1 warps, two pairs per thread, 64x24 tiles
-
+// persistent kernel shapes (render_pk16.cu / render_pk8.cu).  Default: tile 64x16, box 80x20 (zoom up to ~1.19),
+// 5-stage ring, one pixel pair per thread, 16+2 warps; 64x8 tiles with 8+2 warps for small launches (few tiles per
+// SM).  The ring gets shorter when the plane constants of S planes (two tiles' worth) need the room.
 static int pk_cfg()
 {
     static const int v = []() {
@@ -429,23 +381,13 @@ static int pk_cfg()
     return v;
 }
 
-static int tma_cfg()
-{
-    static const int v = []() {
-        const char *e = getenv("MPIFLOW_TMA_CFG");
-        return e ? atoi(e) : 0;
-    }();
-    return v;
-}
-
-// MPIFLOW_RENDER_PATH = pk (default: persistent packed kernel) | tma (per-tile CTAs, scalar) | generic (plain
-// global loads); debugging / A-B measurements only -- tensors a path cannot take fall through to the next
+// MPIFLOW_RENDER_PATH = pk (default: persistent TMA kernel) | generic (plain global loads); debugging / A-B
+// measurements only -- tensors the persistent kernel cannot take fall through to the generic one
 static int render_path()
 {
     static const int v = []() {
         const char *e = getenv("MPIFLOW_RENDER_PATH");
         if (e && strcmp(e, "generic") == 0) return 2;
-        if (e && strcmp(e, "tma") == 0) return 1;
         return 0;
     }();
     return v;
@@ -460,6 +402,22 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
                                          float *out_flow, float *out_obj, void *workspace,
                                          size_t workspace_bytes, int *status, void *stream)
 {
+    return mf_render_fused_impl(rgb, rgb_sb, rgb_ss, rgb_sc, sigma, sig_sb, sig_ss, obj, obj_sb, obj_ss, disparity, G, Kinv,
+                                Kt, B, S, H, W, flags, out_rgb, out_depth, out_mask, out_flow, out_obj, workspace,
+                                workspace_bytes, status, /*clear_status=*/true, (cudaStream_t)stream);
+}
+
+// the same with a choice about the status word: the host-buffer entry point lets the frames of one stream share a
+// sticky flag (cleared once per call) and reads it back once
+int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
+                         const float *sigma, int64_t sig_sb, int64_t sig_ss,
+                         const float *obj, int64_t obj_sb, int64_t obj_ss,
+                         const float *disparity, const float *G, const float *Kinv,
+                         const float *Kt, int B, int S, int H, int W, unsigned flags,
+                         float *out_rgb, float *out_depth, float *out_mask,
+                         float *out_flow, float *out_obj, void *workspace,
+                         size_t workspace_bytes, int *status, bool clear_status, cudaStream_t st)
+{
     MF_CHECK_ARG(rgb && sigma && disparity && G && Kinv && Kt && workspace);
     MF_CHECK_ARG(out_rgb && out_depth && out_mask && out_flow);
     MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0 && B <= 65535 && (int64_t)H * W < (1ll << 31));
@@ -471,14 +429,13 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
     if (workspace_bytes < mpiflow_render_workspace_bytes(B, S)) return MPIFLOW_E_WORKSPACE;
     const size_t smem = (size_t)S * sizeof(PlaneConst);
     MF_CHECK_ARG(smem <= 200 * 1024);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (status) {
+    if (status && clear_status) {
         cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
         if (e != cudaSuccess) return (int)e;
     }
     PlaneConst *pc = reinterpret_cast<PlaneConst *>(workspace);
     BatchConst *bc = reinterpret_cast<BatchConst *>(reinterpret_cast<char *>(workspace) +
-                                                    align_up((size_t)B * S * sizeof(PlaneConst), 256));
+                                                    align_up(((size_t)B * S + 1) * sizeof(PlaneConst), 256));
     int *tile_counter = reinterpret_cast<int *>(reinterpret_cast<char *>(bc) + align_up((size_t)B * sizeof(BatchConst), 256));
     plane_consts_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(G, Kinv, Kt, disparity, B, S, pc, bc, status, tile_counter);
     int rc = mf_launch_status();
@@ -518,28 +475,18 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
         p.flags |= dbg_bits & (MF_FLAG_DBG_NO_LOADS | MF_FLAG_DBG_NO_COMPUTE);
         // few 64x16 tiles per SM (small images / batches): halve the tile so that the persistent CTAs stay balanced
         const long long tiles16 = (long long)((W + 63) / 64) * ((H + 15) / 16) * B;
+        const bool small = tiles16 < 6ll * mf_sm_count();
         switch (pk_cfg()) {
-            case 1: rc = launch_pk<PkTwoPairs>(p, tile_counter, st, &used); break;
-            case 3: rc = launch_pk<PkSmallTile>(p, tile_counter, st, &used); break;
-            case 6: rc = launch_pk<Pk24x2>(p, tile_counter, st, &used); break;
-            case 7: rc = launch_pk<PkWideBox>(p, tile_counter, st, &used); break;
-            case 8: rc = launch_pk<PkNarrowBox>(p, tile_counter, st, &used); break;
-            case 9: rc = launch_pk<PkDefault>(p, tile_counter, st, &used); break;
-            default:
-                rc = tiles16 < 6ll * sm_count() ? launch_pk<PkSmallTile>(p, tile_counter, st, &used)
-                                                : launch_pk<PkDefault>(p, tile_counter, st, &used);
-                break;
+            case 1: case 2: rc = mf_launch_pk_ab(pk_cfg(), p, tile_counter, st, &used); break;
+            case 3: rc = mf_launch_pk8(8, p, tile_counter, st, &used); break;
+            case 9: rc = mf_launch_pk16(5, p, tile_counter, st, &used); break;
+            default: break;
         }
-        if (rc || used) return rc;
-    }
-    if (render_path() <= 1) {
-        bool used = false;
-        switch (tma_cfg()) {
-            case 1: rc = launch_tma<CfgFull>(p, st, &used); break;
-            case 2: rc = launch_tma<CfgNarrow>(p, st, &used); break;
-            case 3: rc = launch_tma<CfgShallow>(p, st, &used); break;
-            default: rc = launch_tma<CfgDefault>(p, st, &used); break;
-        }
+        // the deepest ring that leaves room for the plane constants of S planes
+        if (!rc && !used && small) rc = mf_launch_pk8(8, p, tile_counter, st, &used);
+        if (!rc && !used && small) rc = mf_launch_pk8(4, p, tile_counter, st, &used);
+        if (!rc && !used) rc = mf_launch_pk16(5, p, tile_counter, st, &used);
+        if (!rc && !used) rc = mf_launch_pk16(4, p, tile_counter, st, &used);
         if (rc || used) return rc;
     }
     // generic path: tensors TMA cannot describe (W % 4 != 0, unaligned base, odd strides)
@@ -591,7 +538,7 @@ __global__ void debug_packed_kernel(const float *a, const float *b, const float 
     out[8 * n + i] = u.x; out[8 * n + i + 1] = u.y;
     out[9 * n + i] = __fadd_rn(__fmul_rn(A.x, B.x), -1.f); out[9 * n + i + 1] = __fadd_rn(__fmul_rn(A.y, B.x), -1.f);
     const float2 xe = make_float2(-fabsf(A.x) * (1.f / 22.f), -fabsf(A.y) * (1.f / 22.f));   // down to -95
-    const float2 ee = pk_expf_nonpos(xe);
+    const float2 ee = pk_expf(xe);
     out[10 * n + i] = ee.x; out[10 * n + i + 1] = ee.y;
     out[11 * n + i] = expf(xe.x); out[11 * n + i + 1] = expf(xe.y);
     const float2 qa = make_float2(fabsf(A.x * B.x), fabsf(A.y * B.y));

@@ -290,10 +290,22 @@ MPIFLOW_API int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx,
 
 // ---- host-pointer entry points ----------------------------------------------------------------
 namespace {
+// staging buffer of the host-pointer entry point, per device (the one current at the call); mpiflow_shutdown() frees them
+constexpr int MF_MAX_DEVICES = 64;
 std::mutex g_host_mu;
-void *g_host_buf = nullptr;
-size_t g_host_cap = 0;
+void *g_host_bufs[MF_MAX_DEVICES] = {nullptr};
+size_t g_host_caps[MF_MAX_DEVICES] = {0};
 }  // namespace
+
+void mf_splat_shutdown()
+{
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    for (int d = 0; d < MF_MAX_DEVICES; d++) {
+        if (g_host_bufs[d]) cudaFree(g_host_bufs[d]);
+        g_host_bufs[d] = nullptr;
+        g_host_caps[d] = 0;
+    }
+}
 
 MPIFLOW_API int mpiflow_forward_warp_host(const void *src, const void *idx, const void *idy, const void *z,
                                           void *warped, int h, int w)
@@ -306,6 +318,11 @@ MPIFLOW_API int mpiflow_forward_warp_host(const void *src, const void *idx, cons
     const size_t o_out = o_z + al256(n * 4), o_ws = o_out + al256(n * 5);
     const size_t ws_bytes = mpiflow_forward_warp_workspace_bytes(h, w), need = o_ws + ws_bytes;
     cudaError_t e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e == cudaErrorNoDevice ? MPIFLOW_E_NODEVICE : (int)e;
+    MF_CHECK_ARG(dev >= 0 && dev < MF_MAX_DEVICES);
+    void *&g_host_buf = g_host_bufs[dev];
+    size_t &g_host_cap = g_host_caps[dev];
     if (need > g_host_cap) {
         if (g_host_buf) cudaFree(g_host_buf);
         g_host_buf = nullptr; g_host_cap = 0;

@@ -87,8 +87,11 @@ class SampleWriter:
                 flow, frame, fill = (t.numpy() for t in slot)
                 inpainted = cv2.inpaint(frame, fill, 3, cv2.INPAINT_NS)                      # utils/utils.py:284-286
                 writeFlow(os.path.join(self.out_dir, "flows", f"{name}.flo"), flow)           # gen...v2.py:120
-                cv2.imwrite(os.path.join(self.out_dir, "dst_images", f"{name}.png"), inpainted)
-                cv2.imwrite(os.path.join(self.out_dir, "src_images", f"{name}.png"), src_np)
+                # imwrite reports a full disk / a missing directory / an encoder failure by returning False
+                for sub, img in (("dst_images", inpainted), ("src_images", src_np)):
+                    path = os.path.join(self.out_dir, sub, f"{name}.png")
+                    if not cv2.imwrite(path, img):
+                        raise OSError(f"cv2.imwrite failed for {path}")
             except Exception as e:      # surfaced by the next submit() / close()
                 self._errors.append(e)
             finally:

@@ -136,11 +136,22 @@ def disparity_consistency_src_to_tgt(meshgrid_homo, K_src_inv, disparity_src, G_
 
 
 class _PlaneTag:
-    """Provenance of a plane-derived xyz tensor, so render_tgt_rgb_depth can fuse without reading it."""
-    __slots__ = ("kind", "disparity", "K_inv", "G", "src")
+    """Provenance of a plane-derived xyz tensor, so render_tgt_rgb_depth can fuse without reading it.  The tag also
+    remembers the version counters of the tensor it is attached to and of the tensors it was derived from: an in-place
+    edit of any of them after the fact (xyz[...] += ..., disparity.mul_(...)) invalidates it, and the call takes the
+    un-fused operators, which read the edited values like the reference would."""
+    __slots__ = ("kind", "disparity", "K_inv", "G", "src", "versions")
 
     def __init__(self, kind, disparity=None, K_inv=None, G=None, src=None):
         self.kind, self.disparity, self.K_inv, self.G, self.src = kind, disparity, K_inv, G, src
+        self.versions = ()
+
+    def seal(self, xyz):
+        self.versions = tuple((t, t._version) for t in (xyz, self.disparity, self.K_inv, self.G) if t is not None)
+        return self
+
+    def intact(self):
+        return all(t._version == v for t, v in self.versions)
 
 
 def _same(a, b):
@@ -156,7 +167,7 @@ def get_src_xyz_from_plane_disparity(meshgrid_src_homo, mpi_disparity_src, K_src
     xyz = torch.empty((B, S, 3, H, W), dtype=torch.float32, device=disp.device)
     nat.check(nat.lib().mpiflow_src_xyz_f32(nat.ptr(kinv), nat.ptr(disp), B, S, H, W, nat.ptr(xyz), nat.stream(xyz)))
     xyz = xyz.to(K_src_inv.dtype)
-    xyz._mpiflow_plane = _PlaneTag("src", disparity=mpi_disparity_src, K_inv=K_src_inv)
+    xyz._mpiflow_plane = _PlaneTag("src", disparity=mpi_disparity_src, K_inv=K_src_inv).seal(xyz)
     return xyz
 
 
@@ -168,7 +179,7 @@ def get_tgt_xyz_from_plane_disparity(xyz_src_BS3HW, G_tgt_src):
     out = torch.empty_like(src)
     nat.check(nat.lib().mpiflow_tgt_xyz_f32(nat.ptr(src), nat.ptr(g), B, S, H, W, nat.ptr(out), nat.stream(src)))
     out = out.to(xyz_src_BS3HW.dtype)
-    out._mpiflow_plane = _PlaneTag("tgt", G=G_tgt_src, src=getattr(xyz_src_BS3HW, "_mpiflow_plane", None))
+    out._mpiflow_plane = _PlaneTag("tgt", G=G_tgt_src, src=getattr(xyz_src_BS3HW, "_mpiflow_plane", None)).seal(out)
     return out
 
 
@@ -178,6 +189,7 @@ def get_tgt_xyz_from_plane_disparity(xyz_src_BS3HW, G_tgt_src):
 def _fusable(mpi_disparity_src, xyz_tgt, xyz_src, G_tgt_src, K_src_inv):
     ts, tt = getattr(xyz_src, "_mpiflow_plane", None), getattr(xyz_tgt, "_mpiflow_plane", None)
     return (ts is not None and tt is not None and ts.kind == "src" and tt.kind == "tgt" and tt.src is ts
+            and ts.intact() and tt.intact()
             and _same(ts.disparity, mpi_disparity_src) and _same(ts.K_inv, K_src_inv) and _same(tt.G, G_tgt_src))
 
 

@@ -11,8 +11,12 @@ One dataset sample is, on the device:
                                  (reference: two render_novel_view_dynamic calls, :210-238)
   3. mpiflow_assemble_sample_f32 flow clip, thresholds, merges, u8 conversion (reference: numpy on the host after
                                  eight device->host copies, :239-283)
-and only flow_mix, frame_mix and fill_mask cross PCIe.  Hole filling stays cv2.inpaint on the host (:284-286),
-outside the path.  No CPU fallback: tensors must live on a CUDA device.
+and only flow_mix, frame_mix and fill_mask cross PCIe.  No CPU fallback: tensors must live on a CUDA device.
+
+The module also carries the two loaders and the arrow overlay the generator imports from here
+(gen_3dphoto_dynamic_v2.py:10-14; reference :25-52).  `utils/` has no __init__.py, like the reference's: it is a
+namespace portion, so with this directory first on sys.path `utils.utils` and `utils.mpi.*` resolve here while
+`utils.transform`, `utils.flow_viz`, ... still resolve to the reference's files further down the path.
 """
 import math
 import random
@@ -24,6 +28,33 @@ import _native as nat
 from geometry import transformation_from_parameters
 from utils.mpi import mpi_rendering
 from utils.mpi.homography_sampler import HomographySample
+
+
+def arrowon(img, flow, step=32):
+    """Copy of img with one arrow per step x step cell along the flow (debug overlay); reference :25-32."""
+    import cv2
+    h, w = flow.shape[:2]
+    out = img.copy()
+    for i in range(step // 2, h, step):
+        for j in range(step // 2, w, step):
+            tip = (int(j + flow[i, j, 0]), int(i + flow[i, j, 1]))
+            cv2.arrowedLine(out, (j, i), tip, (0, 0, 255), 2, 8, 0, 0.2)
+    return out
+
+
+def image_to_tensor(img_path, unsqueeze=True):
+    """RGB image file -> float32 [1,]3xHxW in [0,1] (what torchvision's ToTensor gives); reference :35-39."""
+    from PIL import Image
+    rgb = np.array(Image.open(img_path).convert("RGB"), dtype=np.uint8)
+    rgb = torch.from_numpy(rgb).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+    return rgb.unsqueeze(0) if unsqueeze else rgb
+
+
+def disparity_to_tensor(disp_path, unsqueeze=True):
+    """8-bit grey disparity file -> float32 [1,]1xHxW in [0,1] (fp64 division, then rounded); reference :42-52."""
+    import cv2
+    disp = torch.from_numpy(cv2.imread(disp_path, 0) / 255)[None, ...]
+    return (disp.unsqueeze(0) if unsqueeze else disp).float()
 
 
 def gen_swing_path(num_frames=90, r_x=0.14, r_y=0.0, r_z=0.10):
