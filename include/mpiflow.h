@@ -38,6 +38,9 @@ extern "C" {
  * twice): rgb / sigma then hold B/n MPIs, rgb_sb / sig_sb step between MPIs, everything else stays per frame.
  * n = 1..256, B % n == 0.  (A batch stride of 0 says the same for "all B frames share one MPI".) */
 #define MPIFLOW_POSES_PER_MPI(n) ((((unsigned)(n) - 1u) & 0xffu) << 8)
+/* the persistent renderer occupies every SM for the whole launch; n > 0 leaves n SMs free for kernels of other streams
+ * that must make progress meanwhile (a collective gathering the previous step's outputs, shard.FrameGatherer). n = 0..255 */
+#define MPIFLOW_RESERVE_SMS(n) (((unsigned)(n) & 0xffu) << 16)
 
 int mpiflow_version(void);
 /* frees the per-device staging buffers and streams of the host-pointer entry points (they are re-created on the next

@@ -2,6 +2,8 @@
 // plane xyz (a2/a3), plane volume rendering (a7/a8) and alpha composition (a9).
 // One thread per pixel, front-to-back scan over the plane axis held in registers; each input
 // element is read once and each output written once (HBM-bound streaming kernels).
+#include <type_traits>
+
 #include "common.cuh"
 
 // a2: get_src_xyz_from_plane_disparity (mpi_rendering.py:213-239)
@@ -49,6 +51,20 @@ __device__ __forceinline__ float plane_dist(const float *xyz_bs, size_t HW, size
     return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));  // torch.norm(dim=2) (:68-71)
 }
 
+// planes 0..S-1 in order, plane s feeding partial sum s % 4 (the remainder of S / 4 partial sum 0)
+template <class F>
+__device__ __forceinline__ void planes_in_turns(int S, F &plane)
+{
+    int s = 0;
+    for (; s + 4 <= S; s += 4) {
+        plane(s, std::integral_constant<int, 0>{});
+        plane(s + 1, std::integral_constant<int, 1>{});
+        plane(s + 2, std::integral_constant<int, 2>{});
+        plane(s + 3, std::integral_constant<int, 3>{});
+    }
+    for (; s < S; s++) plane(s, std::integral_constant<int, 0>{});
+}
+
 // a7: plane_volume_rendering + weighted_sum_mpi (:62-99, :142-154)
 __global__ void __launch_bounds__(256)
 plane_volume_rendering_kernel(const float *__restrict__ rgb, const float *__restrict__ sigma,
@@ -61,8 +77,12 @@ plane_volume_rendering_kernel(const float *__restrict__ rgb, const float *__rest
     const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (q >= HW) return;
-    float acc = 1.f, wsum = 0.f, r = 0.f, g = 0.f, bl = 0.f, zsum = 0.f, fu = 0.f, fv = 0.f, om = 0.f;
-    for (int s = 0; s < S; s++) {
+    // flow: four partial sums (planes s % 4), combined at the end -- the rounding noise of one sequential fp32 chain over
+    // 64+ planes exceeds 1e-4 at |flow| ~ 200, that of the reference's blocked torch.sum does not (render_pk.cuh)
+    float acc = 1.f, wsum = 0.f, r = 0.f, g = 0.f, bl = 0.f, zsum = 0.f, om = 0.f;
+    float fu[4] = {0.f, 0.f, 0.f, 0.f}, fv[4] = {0.f, 0.f, 0.f, 0.f};
+    auto plane = [&](int s, auto acc_tag) {
+        constexpr int A = decltype(acc_tag)::value;
         const size_t bs = (size_t)b * S + s;
         const float dist = plane_dist(xyz + bs * 3 * HW, HW, q, s, S);
         const float T = expf(-__ldg(sigma + bs * HW + q) * dist);  // :79
@@ -77,11 +97,12 @@ plane_volume_rendering_kernel(const float *__restrict__ rgb, const float *__rest
         bl = fmaf(w, __ldg(c + 2 * HW), bl);
         zsum = fmaf(w, __ldg(xyz + bs * 3 * HW + 2 * HW + q), zsum);
         if (src_flow) {  // :92-96
-            fu = fmaf(w, __ldg(src_flow + bs * 2 * HW + q), fu);
-            fv = fmaf(w, __ldg(src_flow + bs * 2 * HW + HW + q), fv);
+            fu[A] = fmaf(w, __ldg(src_flow + bs * 2 * HW + q), fu[A]);
+            fv[A] = fmaf(w, __ldg(src_flow + bs * 2 * HW + HW + q), fv[A]);
             om = fmaf(w, __ldg(obj + bs * HW + q), om);
         }
-    }
+    };
+    planes_in_turns(S, plane);
     if (rgb_out) {
         float *o = rgb_out + (size_t)b * 3 * HW + q;
         o[0] = r; o[HW] = g; o[2 * HW] = bl;
@@ -90,8 +111,8 @@ plane_volume_rendering_kernel(const float *__restrict__ rgb, const float *__rest
         depth_out[(size_t)b * HW + q] = (flags & MPIFLOW_BG_DEPTH_INF) ? fmaf(1.f - wsum, 1000.f, zsum)
                                                                        : __fdiv_rn(zsum, wsum + 1e-5f);
     if (src_flow && flow_out) {
-        flow_out[(size_t)b * 2 * HW + q] = fu;
-        flow_out[(size_t)b * 2 * HW + HW + q] = fv;
+        flow_out[(size_t)b * 2 * HW + q] = __fadd_rn(__fadd_rn(fu[0], fu[1]), __fadd_rn(fu[2], fu[3]));
+        flow_out[(size_t)b * 2 * HW + HW + q] = __fadd_rn(__fadd_rn(fv[0], fv[1]), __fadd_rn(fv[2], fv[3]));
     }
     if (src_flow && obj_out) obj_out[(size_t)b * HW + q] = om;
 }
@@ -106,8 +127,9 @@ plane_volume_rendering_flow_kernel(const float *__restrict__ sigma, const float 
     const int b = blockIdx.y;
     if (q >= HW) return;
     const bool hard = (flags & MPIFLOW_HARD_FLOW) != 0;
-    float acc = 1.f, fu = 0.f, fv = 0.f, best = -1.f;
-    for (int s = 0; s < S; s++) {
+    float acc = 1.f, best = -1.f, fu[4] = {0.f, 0.f, 0.f, 0.f}, fv[4] = {0.f, 0.f, 0.f, 0.f};
+    auto plane = [&](int s, auto acc_tag) {
+        constexpr int A = decltype(acc_tag)::value;
         const size_t bs = (size_t)b * S + s;
         const float dist = plane_dist(xyz + bs * 3 * HW, HW, q, s, S);
         const float T = expf(-__ldg(sigma + bs * HW + q) * dist);
@@ -115,14 +137,15 @@ plane_volume_rendering_flow_kernel(const float *__restrict__ sigma, const float 
         acc *= (T + 1e-6f);
         const float u = __ldg(flow + bs * 2 * HW + q), v = __ldg(flow + bs * 2 * HW + HW + q);
         if (hard) {  // first arg-max (:126-130)
-            if (w > best) { best = w; fu = u; fv = v; }
+            if (w > best) { best = w; fu[0] = u; fv[0] = v; }
         } else {
-            fu = fmaf(w, u, fu);
-            fv = fmaf(w, v, fv);
+            fu[A] = fmaf(w, u, fu[A]);
+            fv[A] = fmaf(w, v, fv[A]);
         }
-    }
-    flow_out[(size_t)b * 2 * HW + q] = fu;
-    flow_out[(size_t)b * 2 * HW + HW + q] = fv;
+    };
+    planes_in_turns(S, plane);
+    flow_out[(size_t)b * 2 * HW + q] = hard ? fu[0] : __fadd_rn(__fadd_rn(fu[0], fu[1]), __fadd_rn(fu[2], fu[3]));
+    flow_out[(size_t)b * 2 * HW + HW + q] = hard ? fv[0] : __fadd_rn(__fadd_rn(fv[0], fv[1]), __fadd_rn(fv[2], fv[3]));
 }
 
 // a9: alpha_composition (:42-59), C <= 8 channels per launch (host loops over channel groups)

@@ -18,6 +18,9 @@ struct RenderParams {
     float *out_rgb, *out_depth, *out_mask, *out_flow, *out_obj;
     const float *spacing_table;  // [S,H,W] source-frame plane spacing of batch entry 0, or nullptr (render_pk.cuh)
     int poses;                   // consecutive frames per MPI (MPIFLOW_POSES_PER_MPI), >= 1
+    int band_rows;               // image rows per band of the tile queue (render_pk.cuh tile_at); 0 = whole image
+    int reserve_sms;             // SMs the persistent kernel leaves free (MPIFLOW_RESERVE_SMS)
+    float hW, hH, rW, rH;        // W / 2, H / 2 and their fp32 reciprocals (grid normalisation, homography_sampler.py:151-154)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -95,7 +98,7 @@ constexpr float MF_LOG2E = 1.4426950408889634f;
 // front-to-back accumulators of one pixel (mpi_rendering.py:79-96, :143-152)
 struct PixelAcc {
     float acc, r, g, b, zsum, wsum, obj, cnt;  // target frame
-    float acc_s, fu, fv, best_w;               // source frame
+    float acc_s, fu[4], fv[4], best_w;         // source frame: four partial flow sums (planes s % 4)
 };
 // the plane that is still waiting for its successor's geometry (general path only): its thickness is
 // |xyz[s+1] - xyz[s]| evaluated at the two clamped sample positions (:68-71)

@@ -183,10 +183,12 @@ render_fused_kernel(const RenderParams p)
     // plane s-1 waits for plane s's xyz to know its thickness (:68-71)
     float pr = 0.f, pg = 0.f, pb = 0.f, psig = 0.f, pm = 0.f, px = 0.f, py = 0.f, pz = 0.f;
     // source frame
-    float acc_s = 1.f, fu = 0.f, fv = 0.f, best_w = -1.f;
+    // four partial flow sums (planes s % 4), like the persistent kernel: see planes_in_turns in render_pk.cuh
+    float acc_s = 1.f, fu[4] = {0.f, 0.f, 0.f, 0.f}, fv[4] = {0.f, 0.f, 0.f, 0.f}, best_w = -1.f;
     const bool hard = (p.flags & MPIFLOW_HARD_FLOW) != 0;
 
-    for (int s = 0; s < S; s++) {
+    auto plane = [&](int s, auto acc_tag) {
+        constexpr int A = decltype(acc_tag)::value;
         const PlaneConst &c = spc[s];
         // ---------------- target frame ----------------
         const SrcPos sp = tgt_to_src(c.hst, xf, yf, Wf, Hf, rW, rH);
@@ -237,11 +239,21 @@ render_fused_kernel(const RenderParams p)
         const float ws = acc_s * (1.f - Ts);
         acc_s *= (Ts + 1e-6f);
         if (hard) {  // one-hot of the first arg-max weight (:126-130)
-            if (ws > best_w) { best_w = ws; fu = du; fv = dv; }
+            if (ws > best_w) { best_w = ws; fu[0] = du; fv[0] = dv; }
         } else {
-            fu = fmaf(ws, du, fu);
-            fv = fmaf(ws, dv, fv);
+            fu[A] = fmaf(ws, du, fu[A]);
+            fv[A] = fmaf(ws, dv, fv[A]);
         }
+    };
+    {
+        int s = 0;
+        for (; s + 4 <= S; s += 4) {
+            plane(s, std::integral_constant<int, 0>{});
+            plane(s + 1, std::integral_constant<int, 1>{});
+            plane(s + 2, std::integral_constant<int, 2>{});
+            plane(s + 3, std::integral_constant<int, 3>{});
+        }
+        for (; s < S; s++) plane(s, std::integral_constant<int, 0>{});
     }
     t.add(psig, 1e3f, pr, pg, pb, pz, pm);  // last plane: thickness 1e3 (:73-78)
 
@@ -251,8 +263,8 @@ render_fused_kernel(const RenderParams p)
                                           ? fmaf(1.f - t.wsum, 1000.f, t.zsum)      // :148-149
                                           : __fdiv_rn(t.zsum, t.wsum + 1e-5f);      // :151-152
     p.out_mask[(size_t)b * HW + q] = cnt;
-    p.out_flow[(size_t)b * 2 * HW + q] = fu;
-    p.out_flow[(size_t)b * 2 * HW + HW + q] = fv;
+    p.out_flow[(size_t)b * 2 * HW + q] = hard ? fu[0] : __fadd_rn(__fadd_rn(fu[0], fu[1]), __fadd_rn(fu[2], fu[3]));
+    p.out_flow[(size_t)b * 2 * HW + HW + q] = hard ? fv[0] : __fadd_rn(__fadd_rn(fv[0], fv[1]), __fadd_rn(fv[2], fv[3]));
     if (p.out_obj) p.out_obj[(size_t)b * HW + q] = t.obj;
 }
 
@@ -421,10 +433,11 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     MF_CHECK_ARG(rgb && sigma && disparity && G && Kinv && Kt && workspace);
     MF_CHECK_ARG(out_rgb && out_depth && out_mask && out_flow);
     MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0 && B <= 65535 && (int64_t)H * W < (1ll << 31));
-    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW | 0xff00u)) == 0);
+    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW | 0xffff00u)) == 0);
     const int poses = (int)((flags >> 8) & 0xffu) + 1;
+    const int reserve_sms = (int)((flags >> 16) & 0xffu);
     MF_CHECK_ARG(B % poses == 0);
-    flags &= ~0xff00u;
+    flags &= ~0xffff00u;
     MF_CHECK_ARG(((uintptr_t)workspace & 15) == 0);
     if (workspace_bytes < mpiflow_render_workspace_bytes(B, S)) return MPIFLOW_E_WORKSPACE;
     const size_t smem = (size_t)S * sizeof(PlaneConst);
@@ -466,6 +479,19 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     p.out_rgb = out_rgb; p.out_depth = out_depth; p.out_mask = out_mask; p.out_flow = out_flow;
     p.out_obj = out_obj;
     p.spacing_table = table;
+    p.reserve_sms = reserve_sms;
+    p.hW = (float)W * 0.5f; p.hH = (float)H * 0.5f;
+    p.rW = 1.0f / p.hW; p.rH = 1.0f / p.hH;    // IEEE quotients = __frcp_rn: "tensor / python scalar" on CUDA multiplies by this
+    // With the table, the tile queue runs band by band over all frames (render_pk.cuh tile_at): a band's slice of the
+    // table (S * band_rows * W floats, MPIFLOW_PK_BAND_MB, default 16 MB) stays in L2 while the frames pass over it.
+    p.band_rows = 0;
+    if (table) {
+        static const double band_mb = []() { const char *e = getenv("MPIFLOW_PK_BAND_MB"); return e ? atof(e) : 16.0; }();
+        if (band_mb > 0) {
+            const double rows = band_mb * 1048576.0 / ((double)S * W * sizeof(float));
+            p.band_rows = rows >= H ? 0 : (rows < 16 ? 16 : (int)rows / 16 * 16);
+        }
+    }
 
     if (render_path() == 0) {
         bool used = false;

@@ -26,7 +26,8 @@ static int launch_pk(const RenderParams &p, int *tile_counter, cudaStream_t st, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const long long ntiles = (long long)((p.W + Cfg::TW - 1) / Cfg::TW) * ((p.H + Cfg::TH - 1) / Cfg::TH) * p.B;
-    const int grid = (int)(ntiles < mf_sm_count() ? ntiles : mf_sm_count());
+    const int sms = mf_sm_count() - p.reserve_sms > 0 ? mf_sm_count() - p.reserve_sms : 1;
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
     kern<<<grid, Cfg::THREADS, smem, st>>>(m.rgb, m.sig, m.obj, m.sigd, m.dist, p, tile_counter);
     *used = true;
     return mf_launch_status();

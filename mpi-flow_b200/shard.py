@@ -4,9 +4,17 @@ Frames are independent (no halo, no exchange step): rank r renders a contiguous 
 on its own B200; the only collective is the optional gather of the 8 output channels
 (32*H*W bytes per frame) and one max-reduce of the elapsed time.  The reference has no in-process
 equivalent: it runs one generator process per CUDA_VISIBLE_DEVICES (scripts/gen_train_kitti15_v2.sh:1).
+
+Output gather.  `FrameGatherer` owns, per slot, ONE flat send buffer that the renderer's five outputs are views of
+(rgb | depth | mask | flow | obj, each dense) and one receive buffer of `world` such blocks: a step's gather is a
+single `all_gather_into_tensor` of preallocated memory, issued on a side stream behind an event, so the render of
+step i+1 (which writes the other slot) overlaps the gather of step i.  Nothing is allocated, padded or concatenated
+per step; `views(slot)` hands out the gathered frames as per-rank views.
 """
 import torch
 import torch.distributed as dist
+
+CHANNELS = (3, 1, 1, 2, 1)     # rgb, depth, mask (validity count), flowA2B, object mask
 
 
 def shard_range(n_frames, rank, world):
@@ -18,19 +26,84 @@ def shard_range(n_frames, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def gather_frames(local, n_frames, group=None):
-    """all_gather per-rank output slices [n_local, C, H, W] back into batch order [n_frames, C, H, W].
+class FrameGatherer:
+    """Preallocated, overlapped all-gather of the renderer's outputs.
 
-    Works for ragged shards (n_frames not divisible by the world size) by padding to the largest
-    shard; backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
+        g = FrameGatherer(n_frames, H, W, device)          # n_frames = whole batch; this rank renders its shard
+        out = g.outputs(slot)                              # 5 dense tensors [n_local, c, H, W] to render into
+        ... render into out on the current stream ...
+        g.start(slot)                                      # single collective on the side stream
+        ... render the next step into the other slot ...
+        g.wait(slot); per_rank = g.views(slot)             # per channel: list over ranks of [n_r, c, H, W] views
+    """
+
+    def __init__(self, n_frames, H, W, device, slots=2, group=None, channels=CHANNELS, dtype=torch.float32):
+        self.group, self.device = group, torch.device(device)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_frames, self.H, self.W, self.channels = n_frames, H, W, tuple(channels)
+        self.spans = [shard_range(n_frames, r, self.world) for r in range(self.world)]
+        self.longest = max(hi - lo for lo, hi in self.spans)
+        self.n_local = self.spans[self.rank][1] - self.spans[self.rank][0]
+        self.block = self.longest * sum(self.channels) * H * W            # elements per rank (ragged shards padded)
+        self.send = [torch.zeros(self.block, dtype=dtype, device=self.device) for _ in range(slots)]
+        self.recv = [torch.empty(self.world * self.block, dtype=dtype, device=self.device) for _ in range(slots)]
+        self.cuda = self.device.type == "cuda"
+        self.side = torch.cuda.Stream(self.device) if self.cuda else None
+        self.done = [None] * slots
+
+    def _split(self, flat, n):
+        """the five dense per-channel tensors inside one rank's flat block (block layout: rgb | depth | ...)"""
+        out, off = [], 0
+        for c in self.channels:
+            size = self.longest * c * self.H * self.W
+            out.append(flat[off: off + size].view(self.longest, c, self.H, self.W)[:n])
+            off += size
+        return out
+
+    def outputs(self, slot):
+        return self._split(self.send[slot], self.n_local)
+
+    def start(self, slot):
+        """gather slot's send buffer into every rank's receive buffer; returns immediately on CUDA"""
+        if self.cuda:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                dist.all_gather_into_tensor(self.recv[slot], self.send[slot], group=self.group)
+                self.done[slot] = torch.cuda.Event()
+                self.done[slot].record(self.side)
+        else:
+            dist.all_gather_into_tensor(self.recv[slot], self.send[slot], group=self.group)
+
+    def wait(self, slot):
+        """the current stream waits for slot's gather (before its buffers are reused or its views are read)"""
+        if self.cuda and self.done[slot] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.done[slot])
+            self.done[slot] = None
+
+    def views(self, slot):
+        """per channel, the list over ranks of that rank's frames [n_r, c, H, W] (views of the receive buffer)"""
+        per_rank = [self._split(self.recv[slot][r * self.block: (r + 1) * self.block], hi - lo)
+                    for r, (lo, hi) in enumerate(self.spans)]
+        return [[per_rank[r][c] for r in range(self.world)] for c in range(len(self.channels))]
+
+
+def gather_frames(local, n_frames, group=None):
+    """all_gather per-rank output slices [n_local, C, H, W] back into batch order [n_frames, C, H, W] (one
+    `all_gather_into_tensor`; ragged shards are padded to the largest).  Convenience form for one tensor; the
+    benchmark and anything per-step use FrameGatherer, which allocates nothing per call."""
     world = dist.get_world_size(group)
-    sizes = [shard_range(n_frames, r, world) for r in range(world)]
-    longest = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad, group=group)
-    return torch.cat([parts[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    spans = [shard_range(n_frames, r, world) for r in range(world)]
+    longest = max(hi - lo for lo, hi in spans)
+    tail = tuple(local.shape[1:])
+    send = local.new_zeros((longest,) + tail)
+    send[: local.shape[0]] = local
+    recv = local.new_empty((world * longest,) + tail)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    if all(hi - lo == longest for lo, hi in spans):
+        return recv
+    return torch.cat([recv[r * longest: r * longest + hi - lo] for r, (lo, hi) in enumerate(spans)], dim=0)
 
 
 def max_over_ranks(value, device, group=None):

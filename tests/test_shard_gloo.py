@@ -35,8 +35,19 @@ def _worker(rank, world, port, n_frames, out_q):
             if hi > lo else torch.zeros((0, 2, 3, 4))
         whole = shard.gather_frames(local, n_frames)
         slowest = shard.max_over_ranks(1.0 + rank, torch.device("cpu"))
+        # the preallocated gatherer: two steps through two slots, five packed channels, one collective per step
+        g = shard.FrameGatherer(n_frames, 3, 4, "cpu")
+        packed = []
+        for step in range(2):
+            for c, o in enumerate(g.outputs(step)):
+                for i, f in enumerate(range(lo, hi)):
+                    o[i] = 100 * step + 10 * c + f
+            g.start(step)
+        for step in range(2):
+            g.wait(step)
+            packed.append([torch.cat(per_rank, 0).clone() for per_rank in g.views(step)])
         if rank == 0:
-            out_q.put((whole, slowest))
+            out_q.put((whole, slowest, packed))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -50,7 +61,7 @@ def test_two_ranks_gather_in_batch_order(n_frames):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
     for p in procs:
         p.start()
-    whole, slowest = q.get(timeout=120)
+    whole, slowest, packed = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -58,6 +69,13 @@ def test_two_ranks_gather_in_batch_order(n_frames):
     for f in range(n_frames):
         assert torch.equal(whole[f, 0], torch.full((3, 4), float(f)))
         assert torch.equal(whole[f, 1], torch.full((3, 4), float(f) + 1))
+    assert slowest == 2.0
+    for step in range(2):
+        for c, width in enumerate((3, 1, 1, 2, 1)):
+            t = packed[step][c]
+            assert t.shape == (n_frames, width, 3, 4)
+            for f in range(n_frames):
+                assert torch.equal(t[f], torch.full((width, 3, 4), float(100 * step + 10 * c + f)))
     assert slowest == 2.0
 
 
