@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- MPI frames/sec (64 planes, 1280x384) on N B200s; HBM GB/s vs roofline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5-16|c5-32|c5-64|c5-128]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the fused renderer (render_tgt_rgb_depth-equivalent: homography warp of
@@ -12,8 +12,12 @@ config 2 (1x64x384x1280 per frame, random camera pose).  Prints ONE JSON line (r
            buffers in, HOST buffers out, H2D + kernels + D2H inside the timed region
   roofline algorithmic bytes/launch / measured launch time vs the measured HBM copy bandwidth
   cpu_baseline  the CPU oracle timed on this box's host cores on a bounded sample (rank 0, N=1)
---impl reference times the reference's CPU implementation of the same path (torch-CPU operators in
-the reference's order, oracle/torch_ref.py; the reference is Python and cannot travel to this box).
+--impl reference times the reference's own CPU implementation of the same path: the UNMODIFIED utils/mpi/*.py of
+Sharpiless/MPI-Flow (byte copies under oracle/_ref/refsrc/, made by oracle/Makefile) on torch-CPU with all host
+threads, one whole frame per step (kind "reference"); oracle/torch_ref.py, the same operator sequence restated, only
+when those files are absent (kind "port").
+--config selects another BASELINE.json configuration (default c2, the one the metric is quoted on): c3 adds one
+forward splat per frame, c4 is the 256-frame 640x480 batch strong-scaled over the ranks, c5-S the 1920x1080 plane sweep.
 """
 import argparse
 import ctypes
@@ -35,9 +39,25 @@ import torch  # noqa: E402
 import synth  # noqa: E402
 
 METRIC = "MPI frames/sec (64 planes, 1280x384)"
-S, H, W = 64, 384, 1280
-WORKLOAD = "config 2: KITTI-shape 1280x384, 64-plane MPI, random camera pose (synthetic white-noise MPI)"
+# BASELINE.json configurations: planes, height, width, frames per launch per GPU, description
+WORKLOADS = {
+    "c2": (64, 384, 1280, 16, "config 2: KITTI-shape 1280x384, 64-plane MPI, random camera pose (synthetic white-noise MPI)"),
+    "c3": (64, 384, 1280, 16, "config 3: 1280x384, 64 planes + one forward_warping splat per frame (dynamic path)"),
+    "c4": (64, 480, 640, 32, "config 4: batch of 256 COCO-shape 640x480 frames, 64 planes, strong-scaled over the ranks"),
+    "c5-16": (16, 1080, 1920, 4, "config 5: 1920x1080, 16 planes"), "c5-32": (32, 1080, 1920, 4, "config 5: 1920x1080, 32 planes"),
+    "c5-64": (64, 1080, 1920, 4, "config 5: 1920x1080, 64 planes"), "c5-128": (128, 1080, 1920, 2, "config 5: 1920x1080, 128 planes"),
+}
+S, H, W = WORKLOADS["c2"][:3]
+WORKLOAD = WORKLOADS["c2"][4]
 BYTES_PER_FRAME = 4 * H * W * (4 * S + 1 + 8)  # RGBA once + mask once + 8 output channels
+
+
+def set_workload(name):
+    """module-level shape of the run (tools/ import bench for the default, config 2)"""
+    global S, H, W, WORKLOAD, BYTES_PER_FRAME
+    S, H, W, frames, WORKLOAD = WORKLOADS[name]
+    BYTES_PER_FRAME = 4 * H * W * (4 * S + 1 + 8)
+    return frames
 
 
 def measured_peak():
@@ -120,13 +140,13 @@ def make_device_batch(B, seed, device):
 class FusedCall:
     """pre-bound C-ABI call (no per-step allocation): mpiflow_render_fused_f32 on the current stream"""
 
-    def __init__(self, d, device):
+    def __init__(self, d, device, out=None, flags=0):
         import _native as nat
         self.nat, self.L = nat, nat.lib()
         B = d["mpi"].shape[0]
         self.B = B
         new = lambda c: torch.empty((B, c, H, W), dtype=torch.float32, device=device)
-        self.out = (new(3), new(1), new(1), new(2), new(1))
+        self.out = tuple(out) if out is not None else (new(3), new(1), new(1), new(2), new(1))
         self.ws_bytes = self.L.mpiflow_render_workspace_bytes_hw(B, S, H, W)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
@@ -135,11 +155,40 @@ class FusedCall:
         rgb, sig, obj = mpi[:, :, 0:3], mpi[:, :, 3:4], d["obj_mask"]
         p = nat.ptr
         self.args = [p(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), p(sig), sig.stride(0), sig.stride(1),
-                     p(obj), obj.stride(0), 0, p(d["disparity"]), p(d["G"]), p(d["Kinv"]), p(d["K"]), B, S, H, W, 0,
+                     p(obj), obj.stride(0), 0, p(d["disparity"]), p(d["G"]), p(d["Kinv"]), p(d["K"]), B, S, H, W, flags,
                      *[p(o) for o in self.out], p(self.ws), self.ws_bytes, p(self.status)]
+        self.out_arg0 = 19
+
+    def retarget(self, out):
+        """render into other (preallocated) output tensors from now on"""
+        self.out = tuple(out)
+        self.args[self.out_arg0:self.out_arg0 + 5] = [self.nat.ptr(o) for o in self.out]
 
     def __call__(self):
         rc = self.L.mpiflow_render_fused_f32(*self.args, self.nat.stream(self.ws))
+        if rc:
+            self.nat.check(rc)
+
+
+class SplatCall:
+    """pre-bound mpiflow_forward_warp_f32 on one frame's index maps (config 3: moving_obj.py:108-129 per frame)"""
+
+    def __init__(self, device, seed=7):
+        import _native as nat
+        self.nat, self.L = nat, nat.lib()
+        src, idx, idy, z = synth.splat_inputs(H, W, seed, "dense")
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.inp = (t(src), t(idx), t(idy), t(z))
+        self.host = (src, idx, idy, z)
+        self.warped = torch.zeros((H, W, 5), dtype=torch.uint8, device=device)
+        n = self.L.mpiflow_forward_warp_workspace_bytes(H, W)
+        self.ws = torch.empty(n + 256, dtype=torch.uint8, device=device)
+        off = (-self.ws.data_ptr()) % 256
+        self.args = [nat.ptr(x) for x in self.inp] + [nat.ptr(self.warped), H, W, ctypes.c_void_p(self.ws.data_ptr() + off), n]
+
+    def __call__(self):
+        self.warped.zero_()                                  # pre-zeroed by the caller (moving_obj.py:123)
+        rc = self.L.mpiflow_forward_warp_f32(*self.args, self.nat.stream(self.warped))
         if rc:
             self.nat.check(rc)
 
@@ -178,6 +227,42 @@ def sample_assembly_leg(d, steps=24):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def api_leg(d, steps=10):
+    """The same batch through the reference-shaped Python API, in the reference's own call sequence
+    (utils/utils.py:304-331: get_src_xyz_from_plane_disparity -> get_tgt_xyz_from_plane_disparity ->
+    render_tgt_rgb_depth), device-resident, CUDA events.  Reported beside the metric."""
+    try:
+        from utils.mpi import mpi_rendering as R
+        from utils.mpi.homography_sampler import HomographySample
+        check, R.CHECK_SINGULAR = R.CHECK_SINGULAR, False
+        mpi = d["mpi"]
+        B = mpi.shape[0]
+        sampler = HomographySample(H, W, mpi.device)
+        obj = d["obj_mask"].unsqueeze(1).expand(B, S, 1, H, W)
+
+        def one():
+            xyz_src = R.get_src_xyz_from_plane_disparity(sampler.meshgrid, d["disparity"], d["Kinv"])
+            xyz_tgt = R.get_tgt_xyz_from_plane_disparity(xyz_src, d["G"])
+            return R.render_tgt_rgb_depth(sampler, mpi[:, :, 0:3], mpi[:, :, 3:], d["disparity"], xyz_tgt, xyz_src, d["G"],
+                                          d["Kinv"], d["K"], None, use_alpha=False, is_bg_depth_inf=False, obj_mask=obj)
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        R.CHECK_SINGULAR = check
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": round(B / ms * 1e3, 1), "unit": "frames/s", "ms_per_step": round(ms, 4), "steps": steps,
+                "api": "mpi_rendering.get_src_xyz_from_plane_disparity + get_tgt_xyz_from_plane_disparity + "
+                       "render_tgt_rgb_depth (reference call sequence), device-resident, CUDA events"}
+    except Exception as e:  # an auxiliary leg must never take the headline down
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -186,13 +271,23 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     import _native as nat
+    import shard
     L = nat.lib()
     B = args.frames_per_step
-    NBUF = 2
+    strong = args.config == "c4"
+    if strong:
+        # config 4: a fixed batch of 256 frames split over the ranks; a step renders this rank's whole shard in
+        # launches of B frames, cycling over the frames that are resident (up to 64 per GPU, 20 GB)
+        lo, hi = shard.shard_range(256, rank, world)
+        shard_frames = hi - lo
+        launches_per_step = -(-shard_frames // B)
+        NBUF = max(2, min(launches_per_step, 64 // B))
+        frames_per_step_all = 256
+    else:
+        launches_per_step, NBUF, frames_per_step_all = 1, 2, world * B
     calls = [FusedCall(make_device_batch(B, synth.SEED + 1000 * rank + i, device), device) for i in range(NBUF)]
+    splat = SplatCall(device) if args.config == "c3" else None
     peak, peak_src = measured_peak()
-
-    import shard
 
     def barrier():
         if world > 1:
@@ -202,43 +297,63 @@ def run_ours(args, rank, local_rank, world):
     def max_over_ranks(x):
         return x if world == 1 else shard.max_over_ranks(x, device)
 
+    def step(i):
+        for j in range(launches_per_step):
+            calls[(i * launches_per_step + j) % NBUF]()
+        if splat is not None:
+            for _ in range(B):
+                splat()
+
     # ---- device-resident throughput ----
     for i in range(args.warmup):
-        calls[i % NBUF]()
+        step(i)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         barrier()
         ev0.record()
         for i in range(args.steps):
-            calls[i % NBUF]()
+            step(i)
         ev1.record()
         barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     assert int(calls[0].status.item()) == 0
     ms_per_step = ms / args.steps
-    value = world * B * args.steps / (ms * 1e-3)
-    bytes_per_launch = B * BYTES_PER_FRAME
-    achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+    value = frames_per_step_all * args.steps / (ms * 1e-3)
+    frames_per_launch_all = frames_per_step_all / world / launches_per_step     # per GPU and launch
+    bytes_per_launch = frames_per_launch_all * BYTES_PER_FRAME
+    achieved = bytes_per_launch * launches_per_step / (ms_per_step * 1e-3) / 1e9
 
-    # ---- same, with the outputs all_gather'ed to every rank inside the timed region (N > 1) ----
+    # ---- same, with the 8 output channels of every rank gathered to every rank inside the timed region (N > 1) ----
+    # One all_gather_into_tensor per step into preallocated buffers, issued on a side stream while the next step renders
+    # into the other slot; the persistent kernel leaves a few SMs to the collective (MPIFLOW_RESERVE_SMS).
     gather = None
-    if world > 1:
+    if world > 1 and not strong:
         gsteps = min(args.steps, 50)
+        reserve = args.reserve_sms
+        g = shard.FrameGatherer(world * B, H, W, device)
+        gcalls = [FusedCall(c.d, device, out=g.outputs(k % 2), flags=reserve << 16) for k, c in enumerate(calls[:2])]
+
+        def gstep(i):
+            slot = i % 2
+            g.wait(slot)            # the gather that last read this slot's send buffer is done
+            gcalls[slot]()
+            g.start(slot)
+        for i in range(4):
+            gstep(i)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for i in range(gsteps):
-            c = calls[i % NBUF]
-            c()
-            for o in c.out:
-                shard.gather_frames(o, world * B)
+            gstep(i)
+        g.wait(0); g.wait(1)
         g1.record()
         barrier()
         gms = max_over_ranks(g0.elapsed_time(g1))
         gather = {"value": round(world * B * gsteps / (gms * 1e-3), 2), "unit": "frames/s", "steps": gsteps,
-                  "bytes_per_step_per_rank": int(sum(o.numel() * 4 for o in calls[0].out)),
-                  "collective": "NCCL all_gather of the 8 output channels"}
+                  "bytes_per_step_per_rank": int(g.block * 4), "reserved_sms": reserve,
+                  "collective": "one NCCL all_gather_into_tensor of the packed 8 output channels per step, preallocated, "
+                                "on a side stream overlapping the next render"}
 
     # ---- end to end through the host-buffer C-ABI entry point ----
     Be = args.e2e_frames_per_step
@@ -269,46 +384,52 @@ def run_ours(args, rank, local_rank, world):
     h2d = sum(h_in[k].numel() * 4 for k in h_in)
     d2h = sum(o.numel() * 4 for o in h_out)
 
-    sample_leg = sample_assembly_leg(calls[0].d) if (rank == 0 and world == 1) else None
+    solo = rank == 0 and world == 1
+    sample_leg = sample_assembly_leg(calls[0].d) if (solo and args.config == "c2") else None
+    api = api_leg(calls[0].d) if solo else None
 
     # ---- CPU baseline on a bounded sample (rank 0, single-GPU run only) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if solo and not args.no_cpu_baseline:
         cpu = cpu_baseline_c_port()
 
     if rank == 0:
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch of the fused kernel from ncu
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.config in ("c2", "c3"):
             t = json.load(open(tp))
             traffic = t.get("dram_bytes_per_frame", None)
-            traffic = None if traffic is None else traffic * B
+            traffic = None if traffic is None else traffic * frames_per_launch_all
+        launches = (4 if B >= 4 else 3) * launches_per_step + (7 * B if splat is not None else 0)
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "planes": S, "height": H, "width": W, "frames_per_step_per_gpu": B,
-                       "l2": f"inputs {B * S * 4 * H * W * 4 / 1e9:.2f} GB per step (> 126 MB L2), rotated over {NBUF} buffers",
+            "metric": METRIC if args.config == "c2" else f"MPI frames/sec ({S} planes, {W}x{H})",
+            "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "planes": S, "height": H, "width": W, "frames_per_launch_per_gpu": B,
+                       "launches_per_step_per_gpu": launches_per_step,
+                       "l2": f"inputs {B * S * 4 * H * W * 4 / 1e9:.2f} GB per launch (> 126 MB L2), rotated over {NBUF} buffers",
                        "sharding": "frames split across ranks, no data-path collective; NCCL only for barrier/max"},
             "clocks": clk.summary(),
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "frames_per_step_per_gpu": Be, "steps": e2e_steps,
                     "api": "mpiflow_render_fused_host (pinned host buffers)"},
-            # plane_consts + batch_flags (+ spacing_table when >= 4 frames share K^-1 and disparities) + render_fused_pk
-            # per step (profiles/r01_pk_launches.csv)
-            "gpu_launches": (4 if B >= 4 else 3) * args.steps,
+            # per launch: plane_consts + batch_flags (+ spacing_table when >= 4 frames share K^-1 and disparities) +
+            # render_fused_pk; config 3 adds the 7 kernels of one splat per frame
+            "gpu_launches": launches * args.steps,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "kernel": "render_fused_pk_kernel (persistent, warp-specialised; step = prologue + this kernel)",
-                         "bytes_per_launch": bytes_per_launch,
-                         "bound_note": "algorithmic HBM bytes vs measured copy bandwidth; the kernel itself is bound by "
-                                       "instruction issue (DESIGN.md 5.1), not by HBM"},
+                         "bytes_per_launch": int(bytes_per_launch),
+                         "bound_note": "algorithmic HBM bytes vs measured copy bandwidth (DESIGN.md 5.1)"},
             "cpu_baseline": cpu,
         }
         if gather:
             line["with_output_gather"] = gather
         if sample_leg:
             line["sample_assembly"] = sample_leg
+        if api:
+            line["reference_api"] = api
         OUT.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -318,7 +439,7 @@ def run_ours(args, rank, local_rank, world):
 # CPU legs (the only places allowed to execute oracle/)
 # ------------------------------------------------------------------------------------------------
 def _strip_inputs(rows, seed=synth.SEED):
-    """a horizontal strip of the config-2 frame: same width, planes, intrinsics and pose statistics"""
+    """a horizontal strip of the frame: same width, planes, intrinsics and pose statistics"""
     inp = synth.frame_inputs(1, S, rows, W, "white", "random", seed)
     K = synth.intrinsics(H, W, 1)  # intrinsics of the full frame
     inp["K"], inp["Kinv"] = K, synth.intrinsics_inv(K)
@@ -338,41 +459,51 @@ def cpu_baseline_c_port():
     orc.render_frame(inp["mpi"], inp["disparity"], inp["G"], inp["Kinv"], inp["K"], inp["obj_mask"], numerics=1)
     dt = time.perf_counter() - t0
     return {"value": round((rows / H) / dt, 4), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"oracle/mpi_oracle.c (C restatement, OpenMP over {cores} threads), one {W}x{rows}x{S} strip "
+            "sample": f"oracle/mpi_oracle.c (C restatement of the path, OpenMP over {cores} threads), one {W}x{rows}x{S} strip "
                       f"({rows}/{H} of a frame) in {dt:.2f} s"}
 
 
 def run_reference(args, rank):
-    """The reference's CPU path: torch-CPU operators in the reference's order (oracle/torch_ref.py)."""
+    """The reference's own CPU path: its unmodified utils/mpi/*.py (oracle/_ref/refsrc, byte copies made by
+    oracle/Makefile) on torch-CPU with every host thread, one WHOLE frame of the configuration per step."""
     if rank != 0:
         return
-    from oracle import torch_ref
+    from oracle import ref_modules, torch_ref
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     T = torch.from_numpy
+    real = ref_modules.available()
+    render = ref_modules.render_frame if real else torch_ref.render_frame
+    inp = synth.frame_inputs(1, S, H, W, "white", "random", synth.SEED)
+    t = {k: T(v) for k, v in inp.items()}
+    splat_in = synth.splat_inputs(H, W, 7, "dense") if args.config == "c3" else None
 
-    def step(inp):
+    def step():
         t0 = time.perf_counter()
-        torch_ref.render_frame(T(inp["mpi"]), T(inp["disparity"]), T(inp["G"]), T(inp["Kinv"]), T(inp["K"]), T(inp["obj_mask"]))
+        with torch.no_grad():
+            render(t["mpi"], t["disparity"], t["G"], t["Kinv"], t["K"], t["obj_mask"])
+        if splat_in is not None:
+            from oracle import mpi_oracle as orc
+            orc.forward_warping(*splat_in, use_ref=orc.ref_splat_lib() is not None)   # warping.c, serial by construction
         return time.perf_counter() - t0
 
-    step(_strip_inputs(8))
-    per_row = step(_strip_inputs(16)) / 16
-    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
-    rows = int(min(H, max(8, (min(budget, 20.0) / per_row) // 8 * 8)))
-    inp = _strip_inputs(rows)
     for _ in range(args.warmup):
-        step(inp)
-    times = [step(inp) for _ in range(args.steps)]
+        step()
+    times = [step() for _ in range(args.steps)]
     total = sum(times)
-    value = args.steps * (rows / H) / total
-    sample = (f"oracle/torch_ref.py: the reference's operator sequence (matmul, grid_sample, cumprod, exp, norm, sum) "
-              f"on torch-CPU with {cores} threads; each step one {W}x{rows}x{S} strip = {rows}/{H} of a config-2 frame")
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus,
+    value = args.steps / total
+    kind = "reference" if real else "port"
+    what = ("the unmodified utils/mpi/*.py of the reference (oracle/_ref/refsrc): get_src_xyz_from_plane_disparity, "
+            "get_tgt_xyz_from_plane_disparity, render_tgt_rgb_depth" if real else
+            "oracle/torch_ref.py: the reference's operator sequence restated (oracle/_ref/refsrc absent)")
+    sample = f"{what}; torch-CPU, {cores} threads; each step one whole {W}x{H}x{S} frame"
+    line = {"impl": "reference", "metric": METRIC if args.config == "c2" else f"MPI frames/sec ({S} planes, {W}x{H})",
+            "value": round(value, 4), "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / args.steps, 2),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "planes": S, "height": H, "width": W, "strip_rows_per_step": rows},
-            "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": "strong" if args.config == "c4" else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "planes": S, "height": H, "width": W, "frames_per_step": 1},
+            "cpu_baseline": {"value": round(value, 4), "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(value, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     OUT.emit(json.dumps(line))
@@ -406,7 +537,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=16, help="frames per step per GPU (device-resident leg)")
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames-per-step", type=int, default=0, help="frames per launch per GPU (0 = the configuration's own)")
+    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs left to the output gather (with_output_gather leg)")
     ap.add_argument("--e2e-frames-per-step", type=int, default=2)
     ap.add_argument("--e2e-max-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -414,6 +547,8 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    frames = set_workload(args.config)
+    args.frames_per_step = args.frames_per_step or frames
     if args.impl == "reference":
         if args.steps == 200:  # defaults for the slow CPU arm
             args.steps, args.warmup = 3, 1

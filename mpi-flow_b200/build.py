@@ -26,6 +26,16 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines, verbose=False):
+    """development builds of the same library under another name (A/B runs: MPIFLOW_LIB=<path> tools/ab.py ...)"""
+    nvcc = os.environ.get("NVCC", "nvcc")
+    out = os.path.join(HERE, f"libmpiflow_sm100_{name}.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    extra = ["-Xptxas", "-v"] if verbose else []
+    subprocess.check_call([nvcc] + NVCC_FLAGS + extra + [f"-D{d}" for d in defines] + ["-o", out] + srcs)
+    return out
+
+
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mpiflow.h")]
@@ -42,4 +52,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:        # python build.py --variant scalar MPIFLOW_SCALAR_FP MPIFLOW_AB
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if not a.startswith("-")], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

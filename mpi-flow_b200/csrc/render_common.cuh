@@ -18,7 +18,6 @@ struct RenderParams {
     float *out_rgb, *out_depth, *out_mask, *out_flow, *out_obj;
     const float *spacing_table;  // [S,H,W] source-frame plane spacing of batch entry 0, or nullptr (render_pk.cuh)
     int poses;                   // consecutive frames per MPI (MPIFLOW_POSES_PER_MPI), >= 1
-    int band_rows;               // image rows per band of the tile queue (render_pk.cuh tile_at); 0 = whole image
     int reserve_sms;             // SMs the persistent kernel leaves free (MPIFLOW_RESERVE_SMS)
     float hW, hH, rW, rH;        // W / 2, H / 2 and their fp32 reciprocals (grid normalisation, homography_sampler.py:151-154)
 };

@@ -119,7 +119,8 @@ __global__ void spacing_table_kernel(const PlaneConst *__restrict__ pc, const Ba
         const float ex = __fsub_rn(__fmul_rn(r0, dn), __fmul_rn(r0, da));
         const float ey = __fsub_rn(__fmul_rn(r1, dn), __fmul_rn(r1, da));
         const float ez = __fsub_rn(__fmul_rn(r2, dn), __fmul_rn(r2, da));
-        const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+        // torch.norm over the 3-vector on CUDA: ((x^2 + y^2) + z^2) with every square rounded, then sqrt.rn
+        const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
         table[(size_t)s * HW + q] = (s + 1 == S) ? 1e3f : sqrtf(fmaxf(e2, 1e-30f));
     }
 }
@@ -234,7 +235,7 @@ render_fused_kernel(const RenderParams p)
         const float ex = __fsub_rn(__fmul_rn(ray0, c.depth_next), __fmul_rn(ray0, c.depth));
         const float ey = __fsub_rn(__fmul_rn(ray1, c.depth_next), __fmul_rn(ray1, c.depth));
         const float ez = __fsub_rn(__fmul_rn(ray2, c.depth_next), __fmul_rn(ray2, c.depth));
-        const float dist_s = (s + 1 < S) ? sqrtf(__fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)))) : 1e3f;
+        const float dist_s = (s + 1 < S) ? sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez))) : 1e3f;
         const float Ts = expf(__fmul_rn(-__ldg(sig_s + q), dist_s));
         const float ws = acc_s * (1.f - Ts);
         acc_s *= (Ts + 1e-6f);
@@ -482,16 +483,6 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     p.reserve_sms = reserve_sms;
     p.hW = (float)W * 0.5f; p.hH = (float)H * 0.5f;
     p.rW = 1.0f / p.hW; p.rH = 1.0f / p.hH;    // IEEE quotients = __frcp_rn: "tensor / python scalar" on CUDA multiplies by this
-    // With the table, the tile queue runs band by band over all frames (render_pk.cuh tile_at): a band's slice of the
-    // table (S * band_rows * W floats, MPIFLOW_PK_BAND_MB, default 16 MB) stays in L2 while the frames pass over it.
-    p.band_rows = 0;
-    if (table) {
-        static const double band_mb = []() { const char *e = getenv("MPIFLOW_PK_BAND_MB"); return e ? atof(e) : 16.0; }();
-        if (band_mb > 0) {
-            const double rows = band_mb * 1048576.0 / ((double)S * W * sizeof(float));
-            p.band_rows = rows >= H ? 0 : (rows < 16 ? 16 : (int)rows / 16 * 16);
-        }
-    }
 
     if (render_path() == 0) {
         bool used = false;
