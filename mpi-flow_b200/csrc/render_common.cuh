@@ -97,7 +97,7 @@ constexpr float MF_LOG2E = 1.4426950408889634f;
 // front-to-back accumulators of one pixel (mpi_rendering.py:79-96, :143-152)
 struct PixelAcc {
     float acc, r, g, b, zsum, wsum, obj, cnt;  // target frame
-    float acc_s, fu[4], fv[4], best_w;         // source frame: four partial flow sums (planes s % 4)
+    float acc_s, fu, fv, fub, fvb, best_w;     // source frame: flow total and the sum of the current block of four planes
 };
 // the plane that is still waiting for its successor's geometry (general path only): its thickness is
 // |xyz[s+1] - xyz[s]| evaluated at the two clamped sample positions (:68-71)

@@ -4,12 +4,15 @@ positional orders and return tuples: reference :7,42,62,102,142,157,180,213,242,
 Everything heavy runs in libmpiflow_sm100.so.  render_tgt_rgb_depth() -- the generator's hot call,
 utils/utils.py:331 -- is ONE fused sm_100a kernel when its xyz arguments are the plane-derived
 tensors returned by get_src_xyz_from_plane_disparity / get_tgt_xyz_from_plane_disparity (which they
-always are in the reference's callers); for any other xyz tensors the same result is produced by
-the un-fused CUDA operators (warp kernel + compositing kernels).  There is no torch/CPU fallback.
+always are in the reference's callers).  Those two return DEFERRED tensors (_lazy.LazyTensor: right shape,
+dtype and device, values produced by their kernel only if something reads them), so the reference's call
+sequence utils/utils.py:304-331 costs one fused launch and no xyz traffic; for any other xyz tensors the same
+result is produced by the un-fused CUDA operators (warp kernel + compositing kernels).  No torch/CPU fallback.
 """
 import torch
 
 import _native as nat
+from _lazy import LazyTensor
 from utils.mpi.homography_sampler import HomographySample
 from utils.mpi.rendering_utils import transform_G_xyz, sample_pdf, gather_pixel_by_pxpy  # noqa: F401
 
@@ -146,8 +149,10 @@ class _PlaneTag:
         self.kind, self.disparity, self.K_inv, self.G, self.src = kind, disparity, K_inv, G, src
         self.versions = ()
 
-    def seal(self, xyz):
-        self.versions = tuple((t, t._version) for t in (xyz, self.disparity, self.K_inv, self.G) if t is not None)
+    def seal(self, xyz=None):
+        """xyz: the materialised tensor the tag is attached to (a deferred one drops its tag itself when edited)"""
+        self.versions = tuple((t, t._version) for t in (xyz, self.disparity, self.K_inv, self.G)
+                              if t is not None and not isinstance(t, LazyTensor))
         return self
 
     def intact(self):
@@ -155,32 +160,56 @@ class _PlaneTag:
 
 
 def _same(a, b):
-    return a is b or (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.shape == b.shape
-                      and a.data_ptr() == b.data_ptr() and a.stride() == b.stride() and a.dtype == b.dtype)
+    """the same tensor (object or view of the same memory) -- or, when only the dtype differs, a converted copy of it:
+    the generator hands `G.to(K.dtype)` to get_tgt_xyz_from_plane_disparity and `G` itself to render_tgt_rgb_depth
+    (utils/utils.py:308, :331), and in its fp16 mode those are two tensors holding one pose"""
+    if a is b:
+        return True
+    if not (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor)) or a.shape != b.shape or a.device != b.device:
+        return False
+    if a.dtype != b.dtype:
+        return True
+    return a.data_ptr() == b.data_ptr() and a.stride() == b.stride()
 
 
-def get_src_xyz_from_plane_disparity(meshgrid_src_homo, mpi_disparity_src, K_src_inv):
-    """xyz of every plane pixel in the source camera frame -> BxSx3xHxW; reference :213-239."""
+def _src_xyz_now(mpi_disparity_src, K_src_inv, H, W):
     B, S = mpi_disparity_src.shape
-    H, W = meshgrid_src_homo.shape[1:]
     disp, kinv = _dense(mpi_disparity_src, "mpi_disparity_src"), _dense(K_src_inv, "K_src_inv")
     xyz = torch.empty((B, S, 3, H, W), dtype=torch.float32, device=disp.device)
     nat.check(nat.lib().mpiflow_src_xyz_f32(nat.ptr(kinv), nat.ptr(disp), B, S, H, W, nat.ptr(xyz), nat.stream(xyz)))
-    xyz = xyz.to(K_src_inv.dtype)
-    xyz._mpiflow_plane = _PlaneTag("src", disparity=mpi_disparity_src, K_inv=K_src_inv).seal(xyz)
-    return xyz
+    return xyz.to(K_src_inv.dtype)
 
 
-def get_tgt_xyz_from_plane_disparity(xyz_src_BS3HW, G_tgt_src):
-    """The same points in the target camera frame (G . xyz) -> BxSx3xHxW; reference :242-256."""
+def _tgt_xyz_now(xyz_src_BS3HW, G_tgt_src):
     B, S, _, H, W = xyz_src_BS3HW.shape
     G = G_tgt_src if G_tgt_src.dim() == 3 else G_tgt_src.unsqueeze(0)
     src, g = _dense(xyz_src_BS3HW, "xyz_src_BS3HW"), _dense(G.expand(B, 4, 4), "G_tgt_src")
     out = torch.empty_like(src)
     nat.check(nat.lib().mpiflow_tgt_xyz_f32(nat.ptr(src), nat.ptr(g), B, S, H, W, nat.ptr(out), nat.stream(src)))
-    out = out.to(xyz_src_BS3HW.dtype)
-    out._mpiflow_plane = _PlaneTag("tgt", G=G_tgt_src, src=getattr(xyz_src_BS3HW, "_mpiflow_plane", None)).seal(out)
-    return out
+    return out.to(xyz_src_BS3HW.dtype)
+
+
+def get_src_xyz_from_plane_disparity(meshgrid_src_homo, mpi_disparity_src, K_src_inv):
+    """xyz of every plane pixel in the source camera frame -> BxSx3xHxW; reference :213-239.
+    Deferred: the kernel runs when (if) the values are read; render_tgt_rgb_depth does not read them."""
+    B, S = mpi_disparity_src.shape
+    H, W = meshgrid_src_homo.shape[1:]
+    nat.dev(mpi_disparity_src, "mpi_disparity_src"), nat.dev(K_src_inv, "K_src_inv")       # CUDA-only, checked now
+    tag = _PlaneTag("src", disparity=mpi_disparity_src, K_inv=K_src_inv).seal()
+    return LazyTensor(lambda: _src_xyz_now(mpi_disparity_src, K_src_inv, H, W), (B, S, 3, H, W), K_src_inv.dtype,
+                      mpi_disparity_src.device, plane=tag)
+
+
+def get_tgt_xyz_from_plane_disparity(xyz_src_BS3HW, G_tgt_src):
+    """The same points in the target camera frame (G . xyz) -> BxSx3xHxW; reference :242-256.
+    Deferred when xyz_src is the (unedited) deferred tensor of get_src_xyz_from_plane_disparity."""
+    src_tag = getattr(xyz_src_BS3HW, "_mpiflow_plane", None)
+    if isinstance(xyz_src_BS3HW, LazyTensor) and src_tag is not None and src_tag.kind == "src":
+        nat.dev(G_tgt_src, "G_tgt_src")
+        tag = _PlaneTag("tgt", G=G_tgt_src, src=src_tag).seal()
+        return LazyTensor(lambda: _tgt_xyz_now(xyz_src_BS3HW.materialize(), G_tgt_src), xyz_src_BS3HW.shape,
+                          xyz_src_BS3HW.dtype, xyz_src_BS3HW.device, plane=tag)
+    return _tgt_xyz_now(xyz_src_BS3HW, G_tgt_src)
 
 
 # ---------------------------------------------------------------------------------------------
