@@ -384,6 +384,23 @@ def run_ours(args, rank, local_rank, world):
     h2d = sum(h_in[k].numel() * 4 for k in h_in)
     d2h = sum(o.numel() * 4 for o in h_out)
 
+    # ---- the same with the MPI and the mask stored as fp16 on the host (mpiflow_render_fused_host_f16): half the PCIe bytes
+    h16 = {k: src[k][:Be].half().cpu().pin_memory() for k in ("mpi", "obj_mask")}
+    host16_args = [hp(h16["mpi"]), hp(h16["obj_mask"])] + host_args[2:]
+    for _ in range(2):
+        nat.check(L.mpiflow_render_fused_host_f16(*host16_args))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        nat.check(L.mpiflow_render_fused_host_f16(*host16_args))
+    torch.cuda.synchronize()
+    e2e16_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e16 = {"value": round(world * Be * e2e_steps / e2e16_s, 2), "unit": "frames/s",
+             "h2d_bytes_per_step": h2d - sum(h_in[k].numel() * 2 for k in ("mpi", "obj_mask")), "d2h_bytes_per_step": d2h,
+             "frames_per_step_per_gpu": Be, "steps": e2e_steps,
+             "api": "mpiflow_render_fused_host_f16 (fp16 storage of the MPI, fp32 arithmetic and outputs; pinned host buffers)"}
+
     solo = rank == 0 and world == 1
     sample_leg = sample_assembly_leg(calls[0].d) if (solo and args.config == "c2") else None
     api = api_leg(calls[0].d) if solo else None
@@ -414,6 +431,7 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": round(e2e_value, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "frames_per_step_per_gpu": Be, "steps": e2e_steps,
                     "api": "mpiflow_render_fused_host (pinned host buffers)"},
+            "e2e_f16_storage": e2e16,
             # per launch: plane_consts + batch_flags (+ spacing_table when >= 4 frames share K^-1 and disparities) +
             # render_fused_pk; config 3 adds the 7 kernels of one splat per frame
             "gpu_launches": launches * args.steps,

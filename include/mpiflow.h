@@ -85,6 +85,19 @@ int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, i
                              float *out_obj, void *workspace, size_t workspace_bytes, int *status,
                              void *stream);
 
+/* fp16 STORAGE of the same computation: rgb / sigma / obj are IEEE halves (strides in elements), every other argument
+ * and every output as in mpiflow_render_fused_f32; the arithmetic is fp32 on the converted values (parity: identical
+ * to the fp32 entry on the up-cast tensors to rounding of the accumulation order, 1e-4).  Half the HBM / PCIe bytes per
+ * MPI.  Served by the plain global-load kernel (no TMA staging): meant for callers bounded by moving the MPI. */
+int mpiflow_render_fused_f16(const void *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
+                             const void *sigma, int64_t sig_sb, int64_t sig_ss,
+                             const void *obj, int64_t obj_sb, int64_t obj_ss,
+                             const float *disparity, const float *G, const float *Kinv, const float *Kt,
+                             int B, int S, int H, int W, unsigned flags,
+                             float *out_rgb, float *out_depth, float *out_mask, float *out_flow,
+                             float *out_obj, void *workspace, size_t workspace_bytes, int *status,
+                             void *stream);
+
 /* test hook: the shared-reciprocal IEEE division of the kernels, element-wise: qa = a/b, qc = c/b */
 int mpiflow_debug_div_f32(const float *a, const float *c, const float *b, int n, float *qa, float *qc,
                           void *stream);
@@ -106,6 +119,12 @@ int mpiflow_render_fused_host(const float *mpi, const float *obj, const float *d
                               const float *Kinv, const float *Kt, int B, int S, int H, int W,
                               unsigned flags, float *out_rgb, float *out_depth, float *out_mask,
                               float *out_flow, float *out_obj);
+
+/* the same from host buffers holding IEEE halves: mpi [B,S,4,H,W], obj [B,1,H,W] (may be NULL) */
+int mpiflow_render_fused_host_f16(const void *mpi, const void *obj, const float *disparity, const float *G,
+                                  const float *Kinv, const float *Kt, int B, int S, int H, int W,
+                                  unsigned flags, float *out_rgb, float *out_depth, float *out_mask,
+                                  float *out_flow, float *out_obj);
 
 /* ---- fine-grained operators (same maths, un-fused, arbitrary tensors) ---------------------------- */
 /* a4  HomographySample.sample (homography_sampler.py:124-158): src [N,C,H,W] (dense) warped by Hst
@@ -179,6 +198,14 @@ int mpiflow_rasterize_mesh_f32(const float *verts_ndc, const int64_t *faces, con
 int mpiflow_blend_src_f32(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc, const float *sigma,
                           int64_t sig_sb, int64_t sig_ss, const float *src_img, const float *disparity,
                           const float *Kinv, int B, int S, int H, int W, float *out_rgb, void *stream);
+/* fp16 storage of the same step (the generator keeps the MPI and the photograph in half precision,
+ * gen_3dphoto_dynamic_v2.py:82-93): rgb / sigma / src_img are IEEE half (strides in elements), the arithmetic is fp32
+ * on the converted values, and the result is the fp32 MPI mpiflow_render_fused_f32 takes:
+ *   out_mpi [B,S,4,H,W] dense: channels 0..2 the blended colours, channel 3 sigma converted to fp32.
+ * The half MPI is read once; no separate up-cast pass. */
+int mpiflow_blend_src_f16(const void *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc, const void *sigma,
+                          int64_t sig_sb, int64_t sig_ss, const void *src_img, const float *disparity,
+                          const float *Kinv, int B, int S, int H, int W, float *out_mpi, void *stream);
 /* mpiflow_assemble_sample_f32 replaces the host-side thresholds and merges of the two renders of one sample
  * (utils/utils.py:241-283, flow clip :347): frame/mask/flow = outputs of the render with obj_mask, *_dync = outputs
  * of the render with 1 - obj_mask; all channel-planar fp32 [3|1|2,H,W]; obj_mask [H,W].

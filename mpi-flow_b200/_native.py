@@ -29,9 +29,12 @@ _SIGNATURES = {
     "mpiflow_render_workspace_bytes_hw": (_SZ, [_I, _I, _I, _I]),
     "mpiflow_render_fused_f32": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P,
                                       _I, _I, _I, _I, _U, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
+    "mpiflow_render_fused_f16": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P,
+                                      _I, _I, _I, _I, _U, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
     "mpiflow_debug_div_f32": (_I, [_P, _P, _P, _I, _P, _P, _P]),
     "mpiflow_debug_packed_f32": (_I, [_P, _P, _P, _I, _P, _P]),
     "mpiflow_render_fused_host": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _U, _P, _P, _P, _P, _P]),
+    "mpiflow_render_fused_host_f16": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _U, _P, _P, _P, _P, _P]),
     "mpiflow_homography_sample_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "mpiflow_homography_flow_f32": (_I, [_P, _I, _I, _I, _P, _P]),
     "mpiflow_src_xyz_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
@@ -45,6 +48,7 @@ _SIGNATURES = {
     "mpiflow_forward_warp_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "mpiflow_rasterize_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mpiflow_blend_src_f32": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "mpiflow_blend_src_f16": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "mpiflow_assemble_sample_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _c.c_float, _I, _I, _P, _P, _P, _P]),
     "mpiflow_rasterize_mesh_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _P, _P, _P, _P, _P, _SZ, _P]),
 }
@@ -86,6 +90,13 @@ def dev(t, name="tensor"):
     if not t.is_cuda:
         raise RuntimeError(f"{name} is on {t.device}: libmpiflow_sm100 is CUDA-only (no CPU fallback)")
     return t if t.dtype == torch.float32 else t.float()
+
+
+def dev_storage(t, name="tensor"):
+    """like dev(), but an fp16 tensor stays fp16 (the *_f16 entry points read halves); anything else becomes fp32"""
+    if isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float16:
+        return t
+    return dev(t, name)
 
 
 def ptr(t):

@@ -57,12 +57,14 @@ MPIFLOW_API int mpiflow_shutdown(void)
 // Host-buffer variant of mpiflow_render_fused_f32: frames are double-buffered over two streams so
 // the H2D of frame b+1 overlaps the kernels and D2H of frame b (pinned host memory gets full PCIe
 // bandwidth; pageable memory works but is staged by the driver).
-MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, const float *disparity,
-                                          const float *G, const float *Kinv, const float *Kt, int B, int S,
-                                          int H, int W, unsigned flags, float *out_rgb, float *out_depth,
-                                          float *out_mask, float *out_flow, float *out_obj)
+static int render_fused_host(const void *mpi_v, const void *obj_v, size_t es, const float *disparity,
+                             const float *G, const float *Kinv, const float *Kt, int B, int S,
+                             int H, int W, unsigned flags, float *out_rgb, float *out_depth,
+                             float *out_mask, float *out_flow, float *out_obj)
 {
-    MF_CHECK_ARG(mpi && disparity && G && Kinv && Kt && out_rgb && out_depth && out_mask && out_flow);
+    // es = bytes per MPI / mask element: 4 (fp32) or 2 (fp16 storage)
+    const char *mpi = reinterpret_cast<const char *>(mpi_v), *obj = reinterpret_cast<const char *>(obj_v);
+    MF_CHECK_ARG(mpi_v && disparity && G && Kinv && Kt && out_rgb && out_depth && out_mask && out_flow);
     MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0);
     // the host path streams one dense MPI per frame: MPIFLOW_POSES_PER_MPI belongs to the device entry point
     MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW)) == 0);
@@ -77,7 +79,7 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
             return e == cudaErrorNoDevice ? MPIFLOW_E_NODEVICE : (int)e;
 
     const size_t HW = (size_t)H * W;
-    const size_t b_mpi = al256(HW * 4 * S * sizeof(float)), b_obj = al256(HW * sizeof(float));
+    const size_t b_mpi = al256(HW * 4 * S * es), b_obj = al256(HW * es);
     const size_t b_small = al256((S + 16 + 9 + 9) * sizeof(float)), b_out = al256(HW * 8 * sizeof(float));
     const size_t b_ws = al256(mpiflow_render_workspace_bytes(1, S));
     const size_t slot = b_mpi + b_obj + b_small + b_out + b_ws;
@@ -102,14 +104,14 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
     for (int b = 0; b < B; b++) {
         cudaStream_t st = ctx.streams[b & 1];
         char *d = base + (size_t)(b & 1) * slot;
-        float *d_mpi = (float *)d, *d_obj = (float *)(d + b_mpi);
+        char *d_mpi = d, *d_obj = d + b_mpi;
         float *d_small = (float *)(d + b_mpi + b_obj);
         float *d_disp = d_small, *d_G = d_small + S, *d_Kinv = d_G + 16, *d_Kt = d_Kinv + 9;
         float *d_out = (float *)(d + b_mpi + b_obj + b_small);
         void *d_ws = d + b_mpi + b_obj + b_small + b_out;
-        if ((e = cudaMemcpyAsync(d_mpi, mpi + (size_t)b * S * 4 * HW, HW * 4 * S * sizeof(float),
+        if ((e = cudaMemcpyAsync(d_mpi, mpi + (size_t)b * S * 4 * HW * es, HW * 4 * S * es,
                                  cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail((int)e);
-        if (obj) cudaMemcpyAsync(d_obj, obj + (size_t)b * HW, HW * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (obj) cudaMemcpyAsync(d_obj, obj + (size_t)b * HW * es, HW * es, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_disp, disparity + (size_t)b * S, S * sizeof(float), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_G, G + (size_t)b * 16, 16 * sizeof(float), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_Kinv, Kinv + (size_t)b * 9, 9 * sizeof(float), cudaMemcpyHostToDevice, st);
@@ -119,10 +121,10 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
         // status = nullptr: the prologue kernel only ever raises the flag it is given, so the per-stream flag set
         // once above collects every frame of that stream
         const int rc = mf_render_fused_impl(
-            d_mpi, (int64_t)S * 4 * HW, (int64_t)4 * HW, (int64_t)HW, d_mpi + 3 * HW, (int64_t)S * 4 * HW,
-            (int64_t)4 * HW, obj ? d_obj : nullptr, (int64_t)HW, 0, d_disp, d_G, d_Kinv, d_Kt, 1, S, H, W,
-            flags, o_rgb, o_depth, o_mask, o_flow, (obj && out_obj) ? o_obj : nullptr, d_ws, b_ws,
-            d_status + (b & 1), /*clear_status=*/false, st);
+            (const float *)d_mpi, (int64_t)S * 4 * HW, (int64_t)4 * HW, (int64_t)HW, (const float *)(d_mpi + 3 * HW * es),
+            (int64_t)S * 4 * HW, (int64_t)4 * HW, obj ? (const float *)d_obj : nullptr, (int64_t)HW, 0, d_disp, d_G, d_Kinv,
+            d_Kt, 1, S, H, W, flags, o_rgb, o_depth, o_mask, o_flow, (obj && out_obj) ? o_obj : nullptr, d_ws, b_ws,
+            d_status + (b & 1), /*clear_status=*/false, /*f16=*/es == 2, st);
         if (rc) return fail(rc);
         cudaMemcpyAsync(out_rgb + (size_t)b * 3 * HW, o_rgb, 3 * HW * sizeof(float), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(out_depth + (size_t)b * HW, o_depth, HW * sizeof(float), cudaMemcpyDeviceToHost, st);
@@ -137,4 +139,24 @@ MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, co
     int bad[2] = {0, 0};
     if ((e = cudaMemcpy(bad, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return (int)e;
     return (bad[0] | bad[1]) ? MPIFLOW_E_SINGULAR : 0;
+}
+
+MPIFLOW_API int mpiflow_render_fused_host(const float *mpi, const float *obj, const float *disparity,
+                                          const float *G, const float *Kinv, const float *Kt, int B, int S,
+                                          int H, int W, unsigned flags, float *out_rgb, float *out_depth,
+                                          float *out_mask, float *out_flow, float *out_obj)
+{
+    return render_fused_host(mpi, obj, sizeof(float), disparity, G, Kinv, Kt, B, S, H, W, flags, out_rgb, out_depth,
+                             out_mask, out_flow, out_obj);
+}
+
+// fp16 storage from host buffers: mpi [B,S,4,H,W] and obj [B,1,H,W] are IEEE halves -- half the bytes over PCIe, which
+// is what bounds this entry point; everything else (and every output) is fp32
+MPIFLOW_API int mpiflow_render_fused_host_f16(const void *mpi, const void *obj, const float *disparity,
+                                              const float *G, const float *Kinv, const float *Kt, int B, int S,
+                                              int H, int W, unsigned flags, float *out_rgb, float *out_depth,
+                                              float *out_mask, float *out_flow, float *out_obj)
+{
+    return render_fused_host(mpi, obj, 2, disparity, G, Kinv, Kt, B, S, H, W, flags, out_rgb, out_depth, out_mask,
+                             out_flow, out_obj);
 }

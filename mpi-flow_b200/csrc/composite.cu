@@ -48,7 +48,8 @@ __device__ __forceinline__ float plane_dist(const float *xyz_bs, size_t HW, size
     const float *a = xyz_bs + q, *b = a + 3 * HW;  // plane s and s+1
     const float dx = __ldg(b) - __ldg(a), dy = __ldg(b + HW) - __ldg(a + HW),
                 dz = __ldg(b + 2 * HW) - __ldg(a + 2 * HW);
-    return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));  // torch.norm(dim=2) (:68-71)
+    // torch.norm(dim=2) (:68-71) on CUDA: ((x^2 + y^2) + z^2), every square rounded (tools/probe_norm.py), sqrt.rn
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
 
 // planes 0..S-1 in order, plane s feeding partial sum s % 4 (the remainder of S / 4 partial sum 0)

@@ -15,7 +15,13 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "render_launch.cuh"
+
+// storage types of the MPI in the generic kernel: fp32, or fp16 converted on load (fp32 arithmetic either way)
+__device__ __forceinline__ float mf_load(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float mf_load(const __half *p) { return __half2float(__ldg(p)); }
 
 // prologue: PlaneConst for every (b, s); inputs are per batch.
 __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__restrict__ Kinv,
@@ -143,7 +149,9 @@ struct TgtAcc {
     }
 };
 
-template <bool HAS_OBJ>
+// TIn = float: tensors TMA cannot describe.  TIn = __half: the fp16-storage entry point (mpiflow_render_fused_f16):
+// rgb / sigma / obj of RenderParams then point at IEEE halves (strides in elements).
+template <bool HAS_OBJ, class TIn>
 __global__ void __launch_bounds__(256)
 render_fused_kernel(const RenderParams p)
 {
@@ -175,9 +183,9 @@ render_fused_kernel(const RenderParams p)
         ray2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
     }
 
-    const float *rgb_b = p.rgb + (size_t)(b / p.poses) * p.rgb_sb;
-    const float *sig_b = p.sigma + (size_t)(b / p.poses) * p.sig_sb;
-    const float *obj_b = HAS_OBJ ? p.obj + (size_t)b * p.obj_sb : nullptr;
+    const TIn *rgb_b = reinterpret_cast<const TIn *>(p.rgb) + (size_t)(b / p.poses) * p.rgb_sb;
+    const TIn *sig_b = reinterpret_cast<const TIn *>(p.sigma) + (size_t)(b / p.poses) * p.sig_sb;
+    const TIn *obj_b = HAS_OBJ ? reinterpret_cast<const TIn *>(p.obj) + (size_t)b * p.obj_sb : nullptr;
 
     TgtAcc t;
     float cnt = 0.f;
@@ -202,14 +210,14 @@ render_fused_kernel(const RenderParams p)
         const float nw = __fmul_rn(wx1, wy1), ne = __fmul_rn(wx0, wy1);
         const float sw = __fmul_rn(wx1, wy0), se = __fmul_rn(wx0, wy0);
         const int o00 = y0 * W + x0, o01 = y0 * W + x1, o10 = y1 * W + x0, o11 = y1 * W + x1;
-        auto tap = [&](const float *img) {
-            float a = __fmul_rn(__ldg(img + o00), nw);
-            a = __fmaf_rn(__ldg(img + o01), ne, a);
-            a = __fmaf_rn(__ldg(img + o10), sw, a);
-            return __fmaf_rn(__ldg(img + o11), se, a);
+        auto tap = [&](const TIn *img) {
+            float a = __fmul_rn(mf_load(img + o00), nw);
+            a = __fmaf_rn(mf_load(img + o01), ne, a);
+            a = __fmaf_rn(mf_load(img + o10), sw, a);
+            return __fmaf_rn(mf_load(img + o11), se, a);
         };
-        const float *rgb_s = rgb_b + (size_t)s * p.rgb_ss;
-        const float *sig_s = sig_b + (size_t)s * p.sig_ss;
+        const TIn *rgb_s = rgb_b + (size_t)s * p.rgb_ss;
+        const TIn *sig_s = sig_b + (size_t)s * p.sig_ss;
         const float cr = tap(rgb_s), cg = tap(rgb_s + p.rgb_sc), cb = tap(rgb_s + 2 * p.rgb_sc);
         float sg = tap(sig_s);
         const float m = HAS_OBJ ? tap(obj_b + (size_t)s * p.obj_ss) : 0.f;
@@ -236,7 +244,7 @@ render_fused_kernel(const RenderParams p)
         const float ey = __fsub_rn(__fmul_rn(ray1, c.depth_next), __fmul_rn(ray1, c.depth));
         const float ez = __fsub_rn(__fmul_rn(ray2, c.depth_next), __fmul_rn(ray2, c.depth));
         const float dist_s = (s + 1 < S) ? sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez))) : 1e3f;
-        const float Ts = expf(__fmul_rn(-__ldg(sig_s + q), dist_s));
+        const float Ts = expf(__fmul_rn(-mf_load(sig_s + q), dist_s));
         const float ws = acc_s * (1.f - Ts);
         acc_s *= (Ts + 1e-6f);
         if (hard) {  // one-hot of the first arg-max weight (:126-130)
@@ -417,7 +425,25 @@ MPIFLOW_API int mpiflow_render_fused_f32(const float *rgb, int64_t rgb_sb, int64
 {
     return mf_render_fused_impl(rgb, rgb_sb, rgb_ss, rgb_sc, sigma, sig_sb, sig_ss, obj, obj_sb, obj_ss, disparity, G, Kinv,
                                 Kt, B, S, H, W, flags, out_rgb, out_depth, out_mask, out_flow, out_obj, workspace,
-                                workspace_bytes, status, /*clear_status=*/true, (cudaStream_t)stream);
+                                workspace_bytes, status, /*clear_status=*/true, /*f16=*/false, (cudaStream_t)stream);
+}
+
+// fp16 storage: rgb / sigma / obj are IEEE halves (strides in elements), everything else as above; fp32 arithmetic on
+// the converted values.  Served by the plain global-load kernel (half the HBM bytes per tap, no shared-memory staging):
+// it is the entry for callers whose bottleneck is moving the MPI, e.g. over PCIe (mpiflow_render_fused_host_f16).
+MPIFLOW_API int mpiflow_render_fused_f16(const void *rgb, int64_t rgb_sb, int64_t rgb_ss, int64_t rgb_sc,
+                                         const void *sigma, int64_t sig_sb, int64_t sig_ss,
+                                         const void *obj, int64_t obj_sb, int64_t obj_ss,
+                                         const float *disparity, const float *G, const float *Kinv,
+                                         const float *Kt, int B, int S, int H, int W, unsigned flags,
+                                         float *out_rgb, float *out_depth, float *out_mask,
+                                         float *out_flow, float *out_obj, void *workspace,
+                                         size_t workspace_bytes, int *status, void *stream)
+{
+    return mf_render_fused_impl((const float *)rgb, rgb_sb, rgb_ss, rgb_sc, (const float *)sigma, sig_sb, sig_ss,
+                                (const float *)obj, obj_sb, obj_ss, disparity, G, Kinv, Kt, B, S, H, W, flags, out_rgb,
+                                out_depth, out_mask, out_flow, out_obj, workspace, workspace_bytes, status,
+                                /*clear_status=*/true, /*f16=*/true, (cudaStream_t)stream);
 }
 
 // the same with a choice about the status word: the host-buffer entry point lets the frames of one stream share a
@@ -429,7 +455,7 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
                          const float *Kt, int B, int S, int H, int W, unsigned flags,
                          float *out_rgb, float *out_depth, float *out_mask,
                          float *out_flow, float *out_obj, void *workspace,
-                         size_t workspace_bytes, int *status, bool clear_status, cudaStream_t st)
+                         size_t workspace_bytes, int *status, bool clear_status, bool f16, cudaStream_t st)
 {
     MF_CHECK_ARG(rgb && sigma && disparity && G && Kinv && Kt && workspace);
     MF_CHECK_ARG(out_rgb && out_depth && out_mask && out_flow);
@@ -459,7 +485,7 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     // can describe it.  Entries whose K_src^-1 or plane depths differ from entry 0 evaluate it in the plane loop.
     static const bool table_off = []() { const char *e = getenv("MPIFLOW_PK_SPACING_TABLE"); return e && atoi(e) == 0; }();
     const size_t base_bytes = mpiflow_render_workspace_bytes(B, S);
-    const bool have_table = !table_off && render_path() == 0 && B >= 4 && (W % 4) == 0 &&
+    const bool have_table = !f16 && !table_off && render_path() == 0 && B >= 4 && (W % 4) == 0 &&
                             workspace_bytes >= mpiflow_render_workspace_bytes_hw(B, S, H, W);
     float *table = have_table ? reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + base_bytes) : nullptr;
     batch_flags_kernel<<<B, 32, 0, st>>>(pc, bc, S, have_table ? 1 : 0);
@@ -484,7 +510,7 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     p.hW = (float)W * 0.5f; p.hH = (float)H * 0.5f;
     p.rW = 1.0f / p.hW; p.rH = 1.0f / p.hH;    // IEEE quotients = __frcp_rn: "tensor / python scalar" on CUDA multiplies by this
 
-    if (render_path() == 0) {
+    if (render_path() == 0 && !f16) {
         bool used = false;
         static const bool force_literal = []() { const char *e = getenv("MPIFLOW_PK_FORCE_LITERAL"); return e && atoi(e) != 0; }();
         if (force_literal) p.flags |= MF_FLAG_FORCE_LITERAL;
@@ -508,7 +534,8 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     }
     // generic path: tensors TMA cannot describe (W % 4 != 0, unaligned base, odd strides)
     dim3 grid((W + 31) / 32, (H + 7) / 8, B);
-    auto kern = obj ? render_fused_kernel<true> : render_fused_kernel<false>;
+    auto kern = f16 ? (obj ? render_fused_kernel<true, __half> : render_fused_kernel<false, __half>)
+                    : (obj ? render_fused_kernel<true, float> : render_fused_kernel<false, float>);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

@@ -233,7 +233,12 @@ def render_fused(mpi_rgb_src, mpi_sigma_src, mpi_disparity_src, G_tgt_src, K_src
     if not 1 <= poses_per_mpi <= 256:
         raise ValueError("poses_per_mpi must be in 1..256")
     B *= poses_per_mpi
-    rgb, sig = nat.dev(mpi_rgb_src, "mpi_rgb_src"), nat.dev(mpi_sigma_src, "mpi_sigma_src")
+    # an fp16 MPI is read as fp16 (mpiflow_render_fused_f16: fp32 arithmetic on the converted values), never up-cast
+    half = mpi_rgb_src.dtype == torch.float16 and mpi_sigma_src.dtype == torch.float16 and poses_per_mpi == 1
+    if half:
+        rgb, sig = nat.dev_storage(mpi_rgb_src, "mpi_rgb_src"), nat.dev_storage(mpi_sigma_src, "mpi_sigma_src")
+    else:
+        rgb, sig = nat.dev(mpi_rgb_src, "mpi_rgb_src"), nat.dev(mpi_sigma_src, "mpi_sigma_src")
     if not nat.inner_contiguous(rgb):
         rgb = rgb.contiguous()
     if not nat.inner_contiguous(sig):
@@ -250,6 +255,8 @@ def render_fused(mpi_rgb_src, mpi_sigma_src, mpi_disparity_src, G_tgt_src, K_src
     obj_sb = obj_ss = 0
     if obj_mask is not None:
         obj = nat.dev(obj_mask.to(device), "obj_mask")
+        if half:
+            obj = obj.to(torch.float16)       # B x 1 x H x W: the entry point reads one storage type
         while obj.dim() < 5:
             obj = obj.unsqueeze(1)
         obj = obj.expand(B, S, 1, H, W)
@@ -264,7 +271,8 @@ def render_fused(mpi_rgb_src, mpi_sigma_src, mpi_disparity_src, G_tgt_src, K_src
     ws_bytes = L.mpiflow_render_workspace_bytes_hw(B, S, H, W) if B >= 4 else L.mpiflow_render_workspace_bytes(B, S)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
-    nat.check(L.mpiflow_render_fused_f32(
+    entry = L.mpiflow_render_fused_f16 if half else L.mpiflow_render_fused_f32
+    nat.check(entry(
         nat.ptr(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), nat.ptr(sig), sig.stride(0), sig.stride(1),
         nat.ptr(obj), obj_sb, obj_ss, nat.ptr(disp), nat.ptr(G), nat.ptr(kinv), nat.ptr(kt), B, S, H, W,
         _flags(is_bg_depth_inf, hard_flow) | ((poses_per_mpi - 1) << 8), nat.ptr(o_rgb), nat.ptr(o_depth), nat.ptr(o_mask), nat.ptr(o_flow),

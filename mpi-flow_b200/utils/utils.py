@@ -115,23 +115,35 @@ def render_novel_view_dynamic(obj_mask, mpi_all_rgb_src, mpi_all_sigma_src, disp
     return rgb, depth, torch.clip(flow, -200, 200), obj
 
 
-def blend_src_into_mpi(src_imgs, mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, k_src_inv):
+def blend_src_mpi(src_imgs, mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, k_src_inv):
     """blend_weights * src + (1 - blend_weights) * rgb with the source-view blend_weights of the MPI; reference
-    :183-204 -> BxSx3xHxW fp32."""
+    :183-204.  -> (rgb BxSx3xHxW, sigma BxSx1xHxW), fp32, the MPI the renderer takes.
+    An fp16 MPI (the generator's production dtype, gen_3dphoto_dynamic_v2.py:82-93) is read as fp16 by
+    mpiflow_blend_src_f16, which writes blended colours and sigma as ONE fp32 tensor BxSx4xHxW: no up-cast pass; the
+    two results are views of it.  An fp32 MPI keeps its sigma and gets a new BxSx3xHxW colour tensor."""
     B, S, _, H, W = mpi_all_rgb_src.shape
-    rgb, sig = nat.dev(mpi_all_rgb_src, "mpi_all_rgb_src"), nat.dev(mpi_all_sigma_src, "mpi_all_sigma_src")
+    half = mpi_all_rgb_src.dtype == torch.float16 and mpi_all_sigma_src.dtype == torch.float16
+    rgb, sig = nat.dev_storage(mpi_all_rgb_src, "mpi_all_rgb_src"), nat.dev_storage(mpi_all_sigma_src, "mpi_all_sigma_src")
+    if not half:
+        rgb, sig = nat.dev(rgb), nat.dev(sig)
     if not nat.inner_contiguous(rgb):
         rgb = rgb.contiguous()
     if not nat.inner_contiguous(sig):
         sig = sig.contiguous()
-    src = nat.dev(src_imgs, "src_imgs").expand(B, 3, H, W).contiguous()
+    src = nat.dev_storage(src_imgs, "src_imgs") if half else nat.dev(src_imgs, "src_imgs")
+    src = src.to(rgb.dtype).expand(B, 3, H, W).contiguous()
     disp = nat.dev(disparity_all_src, "disparity_all_src").contiguous()
     kinv = nat.dev(k_src_inv.to(rgb.device), "k_src_inv").expand(B, 3, 3).contiguous()
-    out = torch.empty((B, S, 3, H, W), dtype=torch.float32, device=rgb.device)
-    nat.check(nat.lib().mpiflow_blend_src_f32(
-        nat.ptr(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), nat.ptr(sig), sig.stride(0), sig.stride(1),
-        nat.ptr(src), nat.ptr(disp), nat.ptr(kinv), B, S, H, W, nat.ptr(out), nat.stream(rgb)))
-    return out
+    out = torch.empty((B, S, 4 if half else 3, H, W), dtype=torch.float32, device=rgb.device)
+    fn = nat.lib().mpiflow_blend_src_f16 if half else nat.lib().mpiflow_blend_src_f32
+    nat.check(fn(nat.ptr(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), nat.ptr(sig), sig.stride(0), sig.stride(1),
+                 nat.ptr(src), nat.ptr(disp), nat.ptr(kinv), B, S, H, W, nat.ptr(out), nat.stream(rgb)))
+    return (out[:, :, 0:3], out[:, :, 3:4]) if half else (out, sig)
+
+
+def blend_src_into_mpi(src_imgs, mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, k_src_inv):
+    """The blended plane colours alone (BxSx3xHxW fp32); see blend_src_mpi."""
+    return blend_src_mpi(src_imgs, mpi_all_rgb_src, mpi_all_sigma_src, disparity_all_src, k_src_inv)[0]
 
 
 def render_sample_pair(src_imgs, obj_mask, mpi_all_src, disparity_all_src, k_src, k_tgt, cam_ext, cam_ext_dynamic,
@@ -147,7 +159,7 @@ def render_sample_pair(src_imgs, obj_mask, mpi_all_src, disparity_all_src, k_src
     if k_src_inv is None:
         k_src_inv = torch.inverse(k_src.to(torch.float64).cpu()).to(device).to(k_src.dtype)  # :186-187
     mpi_rgb, mpi_sigma = mpi_all_src[:, :, 0:3], mpi_all_src[:, :, 3:]
-    blended = blend_src_into_mpi(src_imgs, mpi_rgb, mpi_sigma, disparity_all_src, k_src_inv)
+    blended, mpi_sigma = blend_src_mpi(src_imgs, mpi_rgb, mpi_sigma, disparity_all_src, k_src_inv)
     obj = nat.dev(obj_mask, "obj_mask").reshape(1, 1, H, W)
     masks = torch.cat((obj, 1 - obj), 0).reshape(2, 1, 1, H, W)                            # :212, :226
     poses = torch.stack((cam_ext.to(device).float(), cam_ext_dynamic.to(device).float()), 0)
@@ -174,7 +186,7 @@ def render_sample_pairs(src_imgs, obj_masks, mpi_all_src, disparity_all_src, k_s
     N, S, _, H, W = mpi_all_src.shape
     device = mpi_all_src.device
     mpi_rgb, mpi_sigma = mpi_all_src[:, :, 0:3], mpi_all_src[:, :, 3:]
-    blended = blend_src_into_mpi(src_imgs, mpi_rgb, mpi_sigma, disparity_all_src, k_src_inv)
+    blended, mpi_sigma = blend_src_mpi(src_imgs, mpi_rgb, mpi_sigma, disparity_all_src, k_src_inv)
     obj = nat.dev(obj_masks, "obj_masks").reshape(N, 1, H, W).contiguous()
     masks = torch.stack((obj, 1 - obj), 1).reshape(2 * N, 1, 1, H, W)
     rgb2, _, _, flow2, obj2 = mpi_rendering.render_fused(
