@@ -11,6 +11,13 @@
 // raster order inside a segment) -> every writer sees its predecessor in the sorted array -> winners
 // are marked independently, the last winner per target is an atomicMax over sorted positions.
 // Everything is integer except the single fp32 '<', so the result is deterministic.
+//
+// ONE launch: the phases (keys + histogram, per pass a scan of the histograms and a stable scatter, resolve, colours)
+// are device functions over "virtual blocks"; splat_fused_kernel is launched cooperatively with as many CTAs as are
+// co-resident and walks them phase by phase with grid-wide barriers (at 1280x384 the seven launches of the unfused
+// form were launch-latency bound: 64 us of which ~10 us were work).  MPIFLOW_SPLAT_FUSED=0 keeps one launch per phase.
+#include <cooperative_groups.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -33,18 +40,19 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;            // items per bl
 // out-of-range targets (undefined behaviour in the reference) get the sentinel n and are dropped.
 // Also: histogram of the first digit per block (digit-major, block-minor), winpos = 0, and zeroing of the
 // histograms of the later passes (the scatter kernels add to them).
-__global__ void __launch_bounds__(SORT_THREADS)
-splat_keys_hist_kernel(const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h, int w, uint32_t n,
-                       int digit_bits, uint32_t nblocks, uint32_t *__restrict__ keys, uint32_t *__restrict__ winpos,
-                       uint32_t *__restrict__ hist0, uint32_t *__restrict__ hist_later, uint32_t hist_later_count)
+// vb / nvb: this virtual block and their number (= blockIdx.x / gridDim.x when every phase is its own launch)
+__device__ __forceinline__ void
+splat_keys_hist(uint32_t vb, uint32_t nvb, const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h, int w, uint32_t n,
+                int digit_bits, uint32_t nblocks, uint32_t *__restrict__ keys, uint32_t *__restrict__ winpos,
+                uint32_t *__restrict__ hist0, uint32_t *__restrict__ hist_later, uint32_t hist_later_count)
 {
     extern __shared__ uint32_t sh[];
     const uint32_t radix = 1u << digit_bits;
     for (uint32_t i = threadIdx.x; i < radix; i += SORT_THREADS) sh[i] = 0;
-    for (uint32_t i = blockIdx.x * SORT_THREADS + threadIdx.x; i < hist_later_count; i += gridDim.x * SORT_THREADS)
+    for (uint32_t i = vb * SORT_THREADS + threadIdx.x; i < hist_later_count; i += nvb * SORT_THREADS)
         hist_later[i] = 0;
     __syncthreads();
-    const uint32_t base = blockIdx.x * SORT_TILE;
+    const uint32_t base = vb * SORT_TILE;
     for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t k = base + r * SORT_THREADS + threadIdx.x;
         if (k < n) {
@@ -57,14 +65,14 @@ splat_keys_hist_kernel(const int64_t *__restrict__ idx, const int64_t *__restric
         }
     }
     __syncthreads();
-    for (uint32_t d = threadIdx.x; d < radix; d += SORT_THREADS) hist0[(size_t)d * nblocks + blockIdx.x] = sh[d];
+    for (uint32_t d = threadIdx.x; d < radix; d += SORT_THREADS) hist0[(size_t)d * nblocks + vb] = sh[d];
 }
 
 // one warp per digit: exclusive scan of that digit's per-block counts (in place) and the digit's total
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_offsets_kernel(uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t radix, uint32_t *__restrict__ totals)
+__device__ __forceinline__ void
+radix_offsets(uint32_t vb, uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t radix, uint32_t *__restrict__ totals)
 {
-    const uint32_t d = blockIdx.x * SORT_WARPS + (threadIdx.x >> 5);
+    const uint32_t d = vb * SORT_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (d >= radix) return;
     uint32_t *row = hist + (size_t)d * nblocks;
@@ -88,12 +96,12 @@ radix_offsets_kernel(uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t rad
 // FIRST: values are the item indices themselves (nothing to read); hist_next != nullptr: count the next digit
 // per destination block.
 template <bool FIRST>
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t n,
-                     int shift, int digit_bits, uint32_t nblocks, const uint32_t *__restrict__ offsets,
-                     const uint32_t *__restrict__ totals, uint32_t *__restrict__ keys_out,
-                     uint32_t *__restrict__ vals_out, uint32_t *__restrict__ hist_next, int next_shift,
-                     int next_bits)
+__device__ __forceinline__ void
+radix_scatter(uint32_t vb, const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t n,
+              int shift, int digit_bits, uint32_t nblocks, const uint32_t *__restrict__ offsets,
+              const uint32_t *__restrict__ totals, uint32_t *__restrict__ keys_out,
+              uint32_t *__restrict__ vals_out, uint32_t *__restrict__ hist_next, int next_shift,
+              int next_bits)
 {
     extern __shared__ uint32_t sh[];
     const uint32_t radix = 1u << digit_bits, mask = radix - 1;
@@ -122,7 +130,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
             if (d0 + i < radix) { dbase[d0 + i] = before; before += totals[d0 + i]; }
     }
     __syncthreads();
-    const uint32_t wbase = blockIdx.x * SORT_TILE + wid * (SORT_ROUNDS * 32);
+    const uint32_t wbase = vb * SORT_TILE + wid * (SORT_ROUNDS * 32);
     uint32_t key[SORT_ROUNDS], val[SORT_ROUNDS], peer[SORT_ROUNDS];   // peer: lanes of this round with the same digit
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
@@ -141,7 +149,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     }
     __syncthreads();
     for (uint32_t d = threadIdx.x; d < radix; d += SORT_THREADS) {
-        uint32_t run = dbase[d] + offsets[(size_t)d * nblocks + blockIdx.x];
+        uint32_t run = dbase[d] + offsets[(size_t)d * nblocks + vb];
 #pragma unroll
         for (int wv = 0; wv < SORT_WARPS; wv++) {
             const uint32_t c = cnt[wv * radix + d];
@@ -171,11 +179,10 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
 }
 
 // every sorted position i: compare with its raster-order predecessor in the same target
-__global__ void splat_resolve_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                     const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ winpos,
-                                     uint8_t *__restrict__ warped)
+__device__ __forceinline__ void splat_resolve(uint32_t i, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                              const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ winpos,
+                                              uint8_t *__restrict__ warped)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t t = keys[i];
     if (t >= n) return;  // dropped (out-of-range target)
@@ -189,10 +196,9 @@ __global__ void splat_resolve_kernel(const uint32_t *__restrict__ keys, const ui
     }
 }
 
-__global__ void splat_rgb_kernel(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ winpos,
-                                 const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ warped)
+__device__ __forceinline__ void splat_rgb(uint32_t t, const uint32_t *__restrict__ vals, const uint32_t *__restrict__ winpos,
+                                          const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ warped)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const uint32_t wp = winpos[t];
     if (!wp) return;
@@ -200,6 +206,88 @@ __global__ void splat_rgb_kernel(const uint32_t *__restrict__ vals, const uint32
     warped[(size_t)t * 5 + 0] = src[(size_t)k * 3 + 0];
     warped[(size_t)t * 5 + 1] = src[(size_t)k * 3 + 1];
     warped[(size_t)t * 5 + 2] = src[(size_t)k * 3 + 2];
+}
+
+// ---- one launch per phase (MPIFLOW_SPLAT_FUSED=0, and whenever a cooperative launch is not possible) ----
+__global__ void __launch_bounds__(SORT_THREADS)
+splat_keys_hist_kernel(const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h, int w, uint32_t n,
+                       int digit_bits, uint32_t nblocks, uint32_t *__restrict__ keys, uint32_t *__restrict__ winpos,
+                       uint32_t *__restrict__ hist0, uint32_t *__restrict__ hist_later, uint32_t hist_later_count)
+{
+    splat_keys_hist(blockIdx.x, gridDim.x, idx, idy, h, w, n, digit_bits, nblocks, keys, winpos, hist0, hist_later, hist_later_count);
+}
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_offsets_kernel(uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t radix, uint32_t *__restrict__ totals)
+{
+    radix_offsets(blockIdx.x, hist, nblocks, radix, totals);
+}
+template <bool FIRST>
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint32_t n,
+                     int shift, int digit_bits, uint32_t nblocks, const uint32_t *__restrict__ offsets,
+                     const uint32_t *__restrict__ totals, uint32_t *__restrict__ keys_out,
+                     uint32_t *__restrict__ vals_out, uint32_t *__restrict__ hist_next, int next_shift,
+                     int next_bits)
+{
+    radix_scatter<FIRST>(blockIdx.x, keys_in, vals_in, n, shift, digit_bits, nblocks, offsets, totals, keys_out, vals_out,
+                         hist_next, next_shift, next_bits);
+}
+__global__ void splat_resolve_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                     const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ winpos,
+                                     uint8_t *__restrict__ warped)
+{
+    splat_resolve(blockIdx.x * blockDim.x + threadIdx.x, keys, vals, z, n, winpos, warped);
+}
+__global__ void splat_rgb_kernel(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ winpos,
+                                 const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ warped)
+{
+    splat_rgb(blockIdx.x * blockDim.x + threadIdx.x, vals, winpos, src, n, warped);
+}
+
+// ---- all phases in one cooperative launch ----
+struct SplatArgs {
+    const uint8_t *src; const int64_t *idx, *idy; const float *z; uint8_t *warped;
+    int h, w; uint32_t n, nblocks; int passes, digit_bits; size_t hist_stride;
+    uint32_t *kA, *vA, *kB, *vB, *winpos, *hist, *totals;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS)
+splat_fused_kernel(const SplatArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t radix = 1u << a.digit_bits;
+    for (uint32_t vb = blockIdx.x; vb < a.nblocks; vb += gridDim.x) {
+        splat_keys_hist(vb, a.nblocks, a.idx, a.idy, a.h, a.w, a.n, a.digit_bits, a.nblocks, a.kA, a.winpos, a.hist,
+                        a.hist + a.hist_stride, (uint32_t)(a.hist_stride * (a.passes - 1)));
+        __syncthreads();      // the shared histogram is reused by the next virtual block
+    }
+    grid.sync();
+    uint32_t *kA = a.kA, *vA = a.vA, *kB = a.kB, *vB = a.vB;
+    for (int p = 0; p < a.passes; p++) {
+        uint32_t *hp = a.hist + (size_t)p * a.hist_stride;
+        const bool more = p + 1 < a.passes;
+        for (uint32_t vb = blockIdx.x; vb < (radix + SORT_WARPS - 1) / SORT_WARPS; vb += gridDim.x)
+            radix_offsets(vb, hp, a.nblocks, radix, a.totals);
+        grid.sync();
+        for (uint32_t vb = blockIdx.x; vb < a.nblocks; vb += gridDim.x) {
+            if (p == 0)
+                radix_scatter<true>(vb, kA, nullptr, a.n, 0, a.digit_bits, a.nblocks, hp, a.totals, kB, vB,
+                                    more ? hp + a.hist_stride : nullptr, a.digit_bits, a.digit_bits);
+            else
+                radix_scatter<false>(vb, kA, vA, a.n, p * a.digit_bits, a.digit_bits, a.nblocks, hp, a.totals, kB, vB,
+                                     more ? hp + a.hist_stride : nullptr, (p + 1) * a.digit_bits, a.digit_bits);
+            __syncthreads();
+        }
+        grid.sync();
+        uint32_t *t = kA; kA = kB; kB = t;
+        t = vA; vA = vB; vB = t;
+    }
+    for (uint32_t i = blockIdx.x * SORT_THREADS + threadIdx.x; i < a.n; i += gridDim.x * SORT_THREADS)
+        splat_resolve(i, kA, vA, a.z, a.n, a.winpos, a.warped);
+    grid.sync();
+    for (uint32_t t = blockIdx.x * SORT_THREADS + threadIdx.x; t < a.n; t += gridDim.x * SORT_THREADS)
+        splat_rgb(t, vA, a.winpos, a.src, a.n, a.warped);
 }
 
 inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
@@ -265,7 +353,27 @@ MPIFLOW_API int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx,
         const int big = (SORT_WARPS + 1) * MAX_RADIX * (int)sizeof(uint32_t);
         cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(splat_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     });
+    static const bool fused_on = []() { const char *e = getenv("MPIFLOW_SPLAT_FUSED"); return !(e && atoi(e) == 0); }();
+    if (fused_on) {
+        // as many CTAs as are co-resident (grid-wide barriers between the phases need all of them on the device)
+        int dev = 0, sms = 0, per_sm = 0, coop = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_fused_kernel, SORT_THREADS, scatter_smem) == cudaSuccess &&
+            per_sm > 0) {
+            SplatArgs a{src, idx, idy, z, warped, h, w, n, L.nblocks, L.passes, db, L.hist_stride, kA, vA, kB, vB, winpos, hist, totals};
+            unsigned grid = (unsigned)(sms * per_sm);
+            if (grid > L.nblocks) grid = L.nblocks;
+            void *args[] = {&a};
+            cudaError_t e = cudaLaunchCooperativeKernel((void *)splat_fused_kernel, dim3(grid), dim3(SORT_THREADS), args,
+                                                        scatter_smem, st);
+            if (e == cudaSuccess) return mf_launch_status();
+            (void)cudaGetLastError();      // not launchable here (e.g. inside a stream capture): one launch per phase
+        }
+    }
     splat_keys_hist_kernel<<<L.nblocks, SORT_THREADS, radix * sizeof(uint32_t), st>>>(
         idx, idy, h, w, n, db, L.nblocks, kA, winpos, hist, hist + L.hist_stride,
         (uint32_t)(L.hist_stride * (L.passes - 1)));
