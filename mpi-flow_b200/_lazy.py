@@ -11,8 +11,9 @@ the kernel that produces its values only when something actually reads them.
     keep the provenance (the generator runs in fp16 and converts its xyz: utils/utils.py:304-309);
   * every other torch function or method materialises the operands first (once; the value is cached) and then runs on
     ordinary tensors -- the result is whatever the reference would have computed;
-  * an in-place operation materialises, applies itself to the cached value and drops the provenance, so a later
-    render_tgt_rgb_depth reads the edited values through the un-fused operators.
+  * an in-place operation materialises and applies itself to the cached value; the value's version counter (shared
+    with every view of it) tells `edited`, so a later render_tgt_rgb_depth reads the edited values through the
+    un-fused operators instead of re-deriving the planes.
 """
 import torch
 
@@ -53,8 +54,13 @@ class LazyTensor(torch.Tensor):
             if isinstance(v, LazyTensor):
                 v = v.materialize()
             assert tuple(v.shape) == tuple(self.shape) and v.dtype == self.dtype, "deferred tensor changed its metadata"
-            self._value, self._thunk = v, None
+            self._value, self._thunk, self._version0 = v, None, v._version
         return self._value
+
+    @property
+    def edited(self):
+        """the materialised values were modified in place (directly or through a view of them) since they were computed"""
+        return self._value is not None and self._value._version != self._version0
 
     def _derived(self, fn, dtype=None):
         """still deferred: fn applied to the value when (if ever) it is needed; same provenance"""

@@ -217,6 +217,8 @@ def get_tgt_xyz_from_plane_disparity(xyz_src_BS3HW, G_tgt_src):
 # ---------------------------------------------------------------------------------------------
 def _fusable(mpi_disparity_src, xyz_tgt, xyz_src, G_tgt_src, K_src_inv):
     ts, tt = getattr(xyz_src, "_mpiflow_plane", None), getattr(xyz_tgt, "_mpiflow_plane", None)
+    if getattr(xyz_src, "edited", False) or getattr(xyz_tgt, "edited", False):
+        return False                       # deferred tensors whose computed values were modified afterwards
     return (ts is not None and tt is not None and ts.kind == "src" and tt.kind == "tgt" and tt.src is ts
             and ts.intact() and tt.intact()
             and _same(ts.disparity, mpi_disparity_src) and _same(ts.K_inv, K_src_inv) and _same(tt.G, G_tgt_src))
