@@ -557,7 +557,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per launch per GPU (0 = the configuration's own)")
-    ap.add_argument("--reserve-sms", type=int, default=16, help="SMs left to the output gather (with_output_gather leg)")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to the output gather (with_output_gather leg)")
     ap.add_argument("--e2e-frames-per-step", type=int, default=2)
     ap.add_argument("--e2e-max-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

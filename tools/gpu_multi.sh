@@ -4,7 +4,7 @@ cd $GRAFT_REPO_ROOT
 N=$1
 run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 "$@"; }
 nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
-for r in 16 0 32; do
+for r in 0 16; do
   run --reserve-sms $r > gpurun_out/bench_n${N}_r$r.log 2>&1
   python - $N $r <<'PY'
 import json,sys
