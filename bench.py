@@ -331,7 +331,7 @@ def run_ours(args, rank, local_rank, world):
     if world > 1 and not strong:
         gsteps = min(args.steps, 50)
         reserve = args.reserve_sms
-        g = shard.FrameGatherer(world * B, H, W, device)
+        g = shard.FrameGatherer(world * B, H, W, device, mode=args.gather)
         gcalls = [FusedCall(c.d, device, out=g.outputs(k % 2), flags=reserve << 16) for k, c in enumerate(calls[:2])]
 
         def gstep(i):
@@ -351,9 +351,17 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         gms = max_over_ranks(g0.elapsed_time(g1))
         gather = {"value": round(world * B * gsteps / (gms * 1e-3), 2), "unit": "frames/s", "steps": gsteps,
-                  "bytes_per_step_per_rank": int(g.block * 4), "reserved_sms": reserve,
-                  "collective": "one NCCL all_gather_into_tensor of the packed 8 output channels per step, preallocated, "
-                                "on a side stream overlapping the next render"}
+                  "bytes_per_step_per_rank": int(g.block * 4), "reserved_sms": reserve, "transport": g.mode,
+                  "why_not_p2p": g.why_not_p2p,
+                  "collective": ("copy-engine pulls of the packed 8 output channels out of the peers' symmetric memory "
+                                 "(one stream per peer, device-side barriers), under the next render" if g.mode == "p2p" else
+                                 "one NCCL all_gather_into_tensor of the packed 8 output channels per step, preallocated, "
+                                 "on a side stream overlapping the next render")}
+        # the gathered frames are the rendered frames (slot 0 of the last even step, every rank's block)
+        if g.mode == "p2p":
+            torch.cuda.synchronize()
+            mine = g.views(0)[0][rank]
+            assert torch.equal(mine, gcalls[0].out[0]), "gathered block differs from the rendered one"
 
     # ---- end to end through the host-buffer C-ABI entry point ----
     Be = args.e2e_frames_per_step
@@ -557,6 +565,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per launch per GPU (0 = the configuration's own)")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"], help="transport of the output-gather leg")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to the output gather (with_output_gather leg)")
     ap.add_argument("--e2e-frames-per-step", type=int, default=2)
     ap.add_argument("--e2e-max-steps", type=int, default=20)

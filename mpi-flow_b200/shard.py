@@ -6,10 +6,16 @@ on its own B200; the only collective is the optional gather of the 8 output chan
 equivalent: it runs one generator process per CUDA_VISIBLE_DEVICES (scripts/gen_train_kitti15_v2.sh:1).
 
 Output gather.  `FrameGatherer` owns, per slot, ONE flat send buffer that the renderer's five outputs are views of
-(rgb | depth | mask | flow | obj, each dense) and one receive buffer of `world` such blocks: a step's gather is a
-single `all_gather_into_tensor` of preallocated memory, issued on a side stream behind an event, so the render of
+(rgb | depth | mask | flow | obj, each dense) and one receive buffer of `world` such blocks, so that the render of
 step i+1 (which writes the other slot) overlaps the gather of step i.  Nothing is allocated, padded or concatenated
-per step; `views(slot)` hands out the gathered frames as per-rank views.
+per step; `views(slot)` hands out the gathered frames as per-rank views.  Two transports:
+
+  * "p2p" (CUDA, peers reachable over NVLink): the send buffers live in symmetric memory
+    (torch.distributed._symmetric_memory); after a device-side barrier every rank PULLS the other ranks' blocks straight
+    out of their memory with copy-engine transfers, one side stream per peer.  No SM is used, so the gather runs under
+    the persistent renderer, which occupies every SM for the whole launch.
+  * "nccl" (and gloo in the CPU tests): a single `all_gather_into_tensor` on a side stream.  NCCL's kernel needs SMs;
+    pass MPIFLOW_RESERVE_SMS(n) to the renderer to leave it some.
 """
 import torch
 import torch.distributed as dist
@@ -37,7 +43,7 @@ class FrameGatherer:
         g.wait(slot); per_rank = g.views(slot)             # per channel: list over ranks of [n_r, c, H, W] views
     """
 
-    def __init__(self, n_frames, H, W, device, slots=2, group=None, channels=CHANNELS, dtype=torch.float32):
+    def __init__(self, n_frames, H, W, device, slots=2, group=None, channels=CHANNELS, dtype=torch.float32, mode="auto"):
         self.group, self.device = group, torch.device(device)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n_frames, self.H, self.W, self.channels = n_frames, H, W, tuple(channels)
@@ -45,11 +51,40 @@ class FrameGatherer:
         self.longest = max(hi - lo for lo, hi in self.spans)
         self.n_local = self.spans[self.rank][1] - self.spans[self.rank][0]
         self.block = self.longest * sum(self.channels) * H * W            # elements per rank (ragged shards padded)
-        self.send = [torch.zeros(self.block, dtype=dtype, device=self.device) for _ in range(slots)]
-        self.recv = [torch.empty(self.world * self.block, dtype=dtype, device=self.device) for _ in range(slots)]
         self.cuda = self.device.type == "cuda"
         self.side = torch.cuda.Stream(self.device) if self.cuda else None
         self.done = [None] * slots
+        self.mode, self.why_not_p2p = "nccl" if self.cuda else dist.get_backend(group), None
+        self.send = None
+        if self.cuda and mode in ("auto", "p2p") and self.world > 1:
+            try:
+                self._setup_p2p(slots, dtype)
+                self.mode = "p2p"
+            except Exception as e:  # noqa: BLE001 -- no symmetric memory / no peer access: the collective still works
+                if mode == "p2p":
+                    raise
+                self.why_not_p2p = f"{type(e).__name__}: {e}"[:200]
+        if self.send is None:
+            self.send = [torch.zeros(self.block, dtype=dtype, device=self.device) for _ in range(slots)]
+        self.recv = [torch.empty(self.world * self.block, dtype=dtype, device=self.device) for _ in range(slots)]
+
+    def _setup_p2p(self, slots, dtype):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        send, handles = [], []
+        for _ in range(slots):
+            t = symm_mem.empty(self.block, dtype=dtype, device=self.device)
+            t.zero_()
+            handles.append(symm_mem.rendezvous(t, grp))
+            send.append(t)
+        # every peer's block of every slot, as tensors in this process's address space (NVLink loads / copy-engine reads)
+        self.peer = [[h.get_buffer(r, (self.block,), dtype) for r in range(self.world)] for h in handles]
+        self.handles = handles
+        self.pull_streams = [torch.cuda.Stream(self.device) for _ in range(self.world - 1)]
+        torch.cuda.synchronize(self.device)
+        handles[0].barrier()
+        torch.cuda.synchronize(self.device)
+        self.send = send
 
     def _split(self, flat, n):
         """the five dense per-channel tensors inside one rank's flat block (block layout: rgb | depth | ...)"""
@@ -65,16 +100,40 @@ class FrameGatherer:
 
     def start(self, slot):
         """gather slot's send buffer into every rank's receive buffer; returns immediately on CUDA"""
-        if self.cuda:
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(self.device))
+        if not self.cuda:
+            dist.all_gather_into_tensor(self.recv[slot], self.send[slot], group=self.group)
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        if self.mode == "p2p":
+            h, recv = self.handles[slot], self.recv[slot]
             with torch.cuda.stream(self.side):
                 self.side.wait_event(ready)
-                dist.all_gather_into_tensor(self.recv[slot], self.send[slot], group=self.group)
+                h.barrier()                      # every rank's block of this slot is rendered
+                fence = torch.cuda.Event()
+                fence.record(self.side)
+            pulled = []
+            for k, st in enumerate(self.pull_streams):      # one copy-engine stream per peer, nearest neighbour first
+                r = (self.rank + 1 + k) % self.world
+                with torch.cuda.stream(st):
+                    st.wait_event(fence)
+                    recv[r * self.block: (r + 1) * self.block].copy_(self.peer[slot][r], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(st)
+                    pulled.append(e)
+            with torch.cuda.stream(self.side):
+                recv[self.rank * self.block: (self.rank + 1) * self.block].copy_(self.send[slot], non_blocking=True)
+                for e in pulled:
+                    self.side.wait_event(e)
+                h.barrier()                      # nobody still reads this rank's block: it may be rendered into again
                 self.done[slot] = torch.cuda.Event()
                 self.done[slot].record(self.side)
-        else:
+            return
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
             dist.all_gather_into_tensor(self.recv[slot], self.send[slot], group=self.group)
+            self.done[slot] = torch.cuda.Event()
+            self.done[slot].record(self.side)
 
     def wait(self, slot):
         """the current stream waits for slot's gather (before its buffers are reused or its views are read)"""

@@ -1,17 +1,15 @@
-# development helper: multi-GPU bench lines (N = $1), incl. the output-gather leg at several SM reservations
+# development helper: multi-GPU bench lines (N = $1), incl. the output-gather leg over both transports
 set -x
 cd $GRAFT_REPO_ROOT
 N=$1
 run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 "$@"; }
-nvidia-smi topo -m > gpurun_out/topo_$N.txt 2>&1
-for r in 0 16; do
-  run --reserve-sms $r > gpurun_out/bench_n${N}_r$r.log 2>&1
-  python - $N $r <<'PY'
+for g in p2p nccl; do
+  run --gather $g > gpurun_out/bench_n${N}_$g.log 2>&1
+  python - $N $g <<'PY'
 import json,sys
 n,r=sys.argv[1:3]
-ls=[x for x in open(f'gpurun_out/bench_n{n}_r{r}.log') if x.startswith('{')]
-if not ls: print(n,r,'NO LINE'); print(open(f'gpurun_out/bench_n{n}_r{r}.log').read()[-2000:]); sys.exit()
-d=json.loads(ls[-1]); print('N',n,'reserve',r,'value',d['value'],'gather',d.get('with_output_gather'),'e2e',d['e2e']['value'],'e2e16',d['e2e_f16_storage']['value'])
+ls=[x for x in open(f'gpurun_out/bench_n{n}_{r}.log') if x.startswith('{')]
+if not ls: print(n,r,'NO LINE'); print(open(f'gpurun_out/bench_n{n}_{r}.log').read()[-3000:]); sys.exit()
+d=json.loads(ls[-1]); print('N',n,'gather',r,'value',d['value'],'gather',d.get('with_output_gather'),'e2e',d['e2e']['value'],'e2e16',d['e2e_f16_storage']['value'])
 PY
 done
-run --config c4 > gpurun_out/bench_n${N}_c4.log 2>&1; grep "^{" gpurun_out/bench_n${N}_c4.log | cut -c1-400
