@@ -523,6 +523,9 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
             case 1: case 2: rc = mf_launch_pk_ab(pk_cfg(), p, tile_counter, st, &used); break;
             case 3: rc = mf_launch_pk8(8, p, tile_counter, st, &used); break;
             case 9: rc = mf_launch_pk16(5, p, tile_counter, st, &used); break;
+            case 4: rc = mf_launch_pk16(15, p, tile_counter, st, &used);      // split warps, A/B
+                    if (!rc && !used) rc = mf_launch_pk16(14, p, tile_counter, st, &used);
+                    break;
             default: break;
         }
         // the deepest ring that leaves room for the plane constants of S planes

@@ -4,6 +4,12 @@
 
 int mf_launch_pk16(int stages, const RenderParams &p, int *tile_counter, cudaStream_t st, bool *used)
 {
+#ifdef MPIFLOW_AB
+    // stages >= 10: the split shape (16 target-frame + 8 source-frame + 2 producer warps), ring of stages - 10; measured
+    // no faster than the default (profiles/r02_experiments.txt), so only development builds instantiate it
+    if (stages >= 15) return launch_pk<PkCfg<64, 16, 80, 20, 5, 1, 1>>(p, tile_counter, st, used);
+    if (stages >= 10) return launch_pk<PkCfg<64, 16, 80, 20, 4, 1, 1>>(p, tile_counter, st, used);
+#endif
     if (stages >= 5) return launch_pk<PkCfg<64, 16, 80, 20, 5, 1>>(p, tile_counter, st, used);
     return launch_pk<PkCfg<64, 16, 80, 20, 4, 1>>(p, tile_counter, st, used);
 }

@@ -121,8 +121,7 @@ class FrameGatherer:
                     e = torch.cuda.Event()
                     e.record(st)
                     pulled.append(e)
-            with torch.cuda.stream(self.side):
-                recv[self.rank * self.block: (self.rank + 1) * self.block].copy_(self.send[slot], non_blocking=True)
+            with torch.cuda.stream(self.side):          # (this rank's own block stays where it was rendered: views())
                 for e in pulled:
                     self.side.wait_event(e)
                 h.barrier()                      # nobody still reads this rank's block: it may be rendered into again
@@ -143,8 +142,9 @@ class FrameGatherer:
 
     def views(self, slot):
         """per channel, the list over ranks of that rank's frames [n_r, c, H, W] (views of the receive buffer)"""
-        per_rank = [self._split(self.recv[slot][r * self.block: (r + 1) * self.block], hi - lo)
-                    for r, (lo, hi) in enumerate(self.spans)]
+        own = self.send[slot] if self.mode == "p2p" else None         # p2p pulls the peers' blocks only
+        per_rank = [self._split(own if (own is not None and r == self.rank) else self.recv[slot][r * self.block: (r + 1) * self.block],
+                                hi - lo) for r, (lo, hi) in enumerate(self.spans)]
         return [[per_rank[r][c] for r in range(self.world)] for c in range(len(self.channels))]
 
 

@@ -1,11 +1,12 @@
-# development helper: one visit to the GPU box
+# development helper: one visit to the GPU box (final records of the round)
 set -x
 cd $GRAFT_REPO_ROOT
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; rc=$?; echo "smoke rc=$rc"; tail -2 gpurun_out/smoke.log
 [ $rc -eq 0 ] || exit 0
-timeout 2400 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest.log
-for m in 0 1 2; do timeout 120 tests/probes/mbar_litmus $m; done > gpurun_out/mbar_litmus.log 2>&1; cat gpurun_out/mbar_litmus.log
-# sanitizers: memcheck on the benchmarked launch shape and the small-shape suites; racecheck on one small render
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest "tests/test_parity_fullsize_gpu.py::test_bench_launch_shape_against_the_unmodified_reference" -m gpu -q -p no:cacheprovider > gpurun_out/memcheck_bench_shape.log 2>&1; echo "memcheck bench-shape rc=$?"; tail -4 gpurun_out/memcheck_bench_shape.log
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_render_gpu.py tests/test_f16_storage_gpu.py tests/test_splat_gpu.py -m gpu -q -p no:cacheprovider -k "not full_size and not properties_at_full and not litmus and not 1280" > gpurun_out/memcheck_small.log 2>&1; echo "memcheck small rc=$?"; tail -4 gpurun_out/memcheck_small.log
-timeout 900 compute-sanitizer --tool racecheck python -m pytest "tests/test_render_gpu.py::test_batch_entries_are_independent" -m gpu -q -p no:cacheprovider > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; grep -c "hazard" gpurun_out/racecheck.log; grep "RACECHECK SUMMARY" gpurun_out/racecheck.log; grep -A3 "hazard detected" gpurun_out/racecheck.log | grep " at \|hazard" | sort | uniq -c | sort -rn | head -20
+timeout 2400 python -m pytest tests -m gpu -q --maxfail=40 -p no:cacheprovider > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_20.log 2>&1; grep "^{" gpurun_out/r02_bench_20.log | cut -c1-250
+timeout 900 python bench.py --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/r02_bench_200.log 2>&1; grep "^{" gpurun_out/r02_bench_200.log | cut -c1-250
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference.log 2>&1; grep "^{" gpurun_out/r02_bench_reference.log | cut -c1-400
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file gpurun_out/r02_pk_launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; tail -3 gpurun_out/r02_pk_launches.csv | cut -c1-300
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_fused_pk -s 2 -c 1 -o gpurun_out/r02_pk -f python tools/pk_once.py 16 4 > gpurun_out/ncu.log 2>&1; tail -2 gpurun_out/ncu.log
+timeout 600 python tools/sample_bench.py > gpurun_out/r02_sample_bench.log 2>&1; tail -3 gpurun_out/r02_sample_bench.log | cut -c1-400
