@@ -6,8 +6,9 @@ snapshot, where /root/reference does not exist).  This module imports those file
 that the reference's own `from utils.mpi... import` lines resolve to the reference's files and not to the
 product's modules of the same names, and leaves sys.modules / sys.path as it found them.
 
-On a CUDA box the reference runs unshimmed (its inverse() hard-codes .cuda(), homography_sampler.py:15-17); on a
-CPU-only box the two calls are shimmed for the duration of a call with cpu_shims().
+On CUDA tensors the reference runs unshimmed (its inverse() hard-codes .cuda(), homography_sampler.py:15-17); on CPU
+tensors -- CPU-only box, or the CPU reference arm of bench.py on the GPU box -- the two calls are shimmed for the
+duration of a call with cpu_shims().
 
 Only tests/, __graft_entry__.smoke() and bench.py's reference / cpu_baseline legs may import this.
 """
@@ -57,9 +58,13 @@ def load():
 
 
 @contextlib.contextmanager
-def cpu_shims():
-    """The reference's inverse() calls .cuda() and torch.cuda.synchronize(); make both no-ops on a CPU-only box."""
-    if torch.cuda.is_available():
+def cpu_shims(active=None):
+    """The reference's inverse() calls .cuda() and torch.cuda.synchronize() (homography_sampler.py:15-17); for a run on
+    CPU tensors both are made no-ops -- on a CPU-only box, and on the GPU box when the reference's CPU path is what is
+    being timed (bench.py --impl reference).  active=None: shim iff there is no CUDA device."""
+    if active is None:
+        active = not torch.cuda.is_available()
+    if not active:
         yield
         return
     sync, cuda = torch.cuda.synchronize, torch.Tensor.cuda
@@ -78,7 +83,7 @@ def render_frame(mpi, disparity, G, Kinv, K, obj_mask=None, is_bg_depth_inf=Fals
     -> (rgb, depth, mask, flowA2B, obj)."""
     R, HS, _, _ = load()
     B, S, _, H, W = mpi.shape
-    with cpu_shims():
+    with cpu_shims(active=mpi.device.type == "cpu"):
         sampler = HS.HomographySample(H, W, mpi.device)
         xyz_src = R.get_src_xyz_from_plane_disparity(sampler.meshgrid, disparity, Kinv)
         xyz_tgt = R.get_tgt_xyz_from_plane_disparity(xyz_src, G)

@@ -142,3 +142,24 @@ def test_unmodified_generator_runs_in_half_precision(tmp_path):
             assert np.abs(dst.astype(np.int32) - src.astype(np.int32)).mean() < 40
         if name == "a":
             assert np.abs(src.astype(np.int32) - src_in.astype(np.int32)).max() <= 1    # fp16 round trip of the image
+
+
+def test_reference_modules_run_on_cpu_tensors_even_where_cuda_exists(monkeypatch):
+    """bench.py --impl reference times the reference's CPU path ON THE GPU BOX: its inverse() hard-codes .cuda()
+    (homography_sampler.py:15-17), so the shims have to follow the tensors' device, not the machine's."""
+    import torch
+    import synth
+    from oracle import ref_modules, torch_ref
+    if not ref_modules.available():
+        pytest.skip("oracle/_ref/refsrc is built by `make -C oracle ref` in the build container")
+    inp = {k: torch.from_numpy(v) for k, v in synth.frame_inputs(1, 4, 24, 32, "smooth", "random", 3).items()}
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+
+    def no_cuda(self, *a, **k):
+        raise AssertionError("a CPU run of the reference must not move tensors to CUDA")
+    monkeypatch.setattr(torch.Tensor, "cuda", no_cuda)
+    out = ref_modules.render_frame(inp["mpi"], inp["disparity"], inp["G"], inp["Kinv"], inp["K"], inp["obj_mask"])
+    want = torch_ref.render_frame(inp["mpi"], inp["disparity"], inp["G"], inp["Kinv"], inp["K"], inp["obj_mask"])
+    for a, b in zip(out, want):
+        assert torch.equal(a, b)
+    assert torch.Tensor.cuda is no_cuda          # restored after the call
