@@ -215,6 +215,18 @@ int mpiflow_assemble_sample_f32(const float *frame, const float *frame_dync, con
                                 const float *obj_mask, float mask_thresh, int H, int W, float *flow_mix,
                                 unsigned char *frame_mix, unsigned char *fill_mask, void *stream);
 
+/* ---- hole filling of the assembled sample ---------------------------------------------
+ * mpiflow_inpaint_ns_u8 replaces cv2.inpaint(frame_mix, fill_mask, 3, cv2.INPAINT_NS) (reference utils/utils.py:284-286;
+ * OpenCV is an un-vendored dependency of the reference): OpenCV's fast-marching Navier-Stokes inpainting, BIT FOR BIT
+ * (same arrival order, same fp32 / fp64 steps; oracle/inpaint_oracle.c restates it and is pinned against cv2.inpaint).
+ * A batch of n independent images per call, one warp marching each image.
+ *   img  u8 [n,rows,cols,3] (interleaved, as cv2), mask u8 [n,rows,cols] (non-zero = to fill), radius 1..5
+ *   out  u8 [n,rows,cols,3]; may be img itself (in place)
+ *   workspace: mpiflow_inpaint_ns_workspace_bytes(n, rows, cols) bytes, 256-byte aligned; no allocation, no sync */
+size_t mpiflow_inpaint_ns_workspace_bytes(int n, int rows, int cols);
+int mpiflow_inpaint_ns_u8(const uint8_t *img, const uint8_t *mask, int n, int rows, int cols, int radius,
+                          uint8_t *out, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "mpiflow_blend_src_f32": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "mpiflow_blend_src_f16": (_I, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "mpiflow_assemble_sample_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _c.c_float, _I, _I, _P, _P, _P, _P]),
+    "mpiflow_inpaint_ns_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "mpiflow_inpaint_ns_u8": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "mpiflow_rasterize_mesh_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _c.c_float, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpiflow_sm100.so")
 WARPLIB = os.path.join(HERE, "external", "forward_warping", "libwarping.so")
 SOURCES = ["api.cu", "homography.cu", "render_fused.cu", "render_pk16.cu", "render_pk8.cu", "composite.cu", "splat.cu",
-           "raster.cu", "assemble.cu"]
+           "raster.cu", "assemble.cu", "inpaint.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static", "--threads", "0"]
 

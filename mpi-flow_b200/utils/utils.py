@@ -205,12 +205,40 @@ def render_sample_pairs(src_imgs, obj_masks, mpi_all_src, disparity_all_src, k_s
     return flow_mix, frame_mix, fill_mask
 
 
+_inpaint_ws = {}     # (device index, n, H, W) -> workspace tensor; reused across samples, never shrunk
+
+
+def inpaint_ns(frame, fill_mask, radius=3, out=None):
+    """cv2.inpaint(frame, fill_mask, radius, cv2.INPAINT_NS) (reference :284-286) on the device, bit for bit:
+    frame u8 [H,W,3] or [N,H,W,3] (interleaved, as cv2 takes it), fill_mask u8 [H,W] or [N,H,W] (non-zero = fill).
+    -> u8 tensor of frame's shape (out=frame fills in place).  A batch marches its N images on N warps of one
+    launch (csrc/inpaint.cu); no host synchronisation."""
+    if not (isinstance(frame, torch.Tensor) and frame.is_cuda and isinstance(fill_mask, torch.Tensor) and fill_mask.is_cuda):
+        raise RuntimeError("inpaint_ns: frame and fill_mask must be CUDA tensors (no CPU fallback)")
+    if frame.dtype != torch.uint8 or fill_mask.dtype != torch.uint8:
+        raise TypeError("inpaint_ns: uint8 image and mask, like cv2.inpaint")
+    single = frame.dim() == 3
+    img = (frame.unsqueeze(0) if single else frame).contiguous()
+    msk = (fill_mask.unsqueeze(0) if single else fill_mask).contiguous()
+    N, H, W, C = img.shape
+    if C != 3 or tuple(msk.shape) != (N, H, W):
+        raise ValueError(f"inpaint_ns: image {tuple(frame.shape)} / mask {tuple(fill_mask.shape)}")
+    L = nat.lib()
+    key = (img.device.index, N, H, W)
+    ws = _inpaint_ws.get(key)
+    if ws is None:
+        ws = torch.empty(L.mpiflow_inpaint_ns_workspace_bytes(N, H, W), dtype=torch.uint8, device=img.device)
+        _inpaint_ws[key] = ws
+    res = img if (out is frame and img.data_ptr() == frame.data_ptr()) else torch.empty_like(img)
+    nat.check(L.mpiflow_inpaint_ns_u8(nat.ptr(img), nat.ptr(msk), N, H, W, int(round(radius)), nat.ptr(res), nat.ptr(ws),
+                                      ws.numel(), nat.stream(img)))
+    return res[0] if single else res
+
+
 def render_3dphoto_dynamic(opt, src_imgs, obj_mask, disp, mpi_all_src, disparity_all_src, k_src, k_tgt,
                            data_path=None, name=None, hard_flow=False, mask_thresh=0.99):
     """One training pair from one MPI: -> (flow_mix HxWx2 f32, src_np HxWx3 u8 BGR, inpainted HxWx3 u8 BGR, None);
     reference :159-288.  `disp`, `data_path` and `name` are unused there too (name only has its suffix cut)."""
-    import cv2  # host-side hole filling only; outside the device path
-
     if name is not None:
         name = name.split(".")[0]
     src_np = (nat.dev(src_imgs, "src_imgs")[0].permute(1, 2, 0) * 255).round().clamp(0, 255).to(torch.uint8)
@@ -221,6 +249,5 @@ def render_3dphoto_dynamic(opt, src_imgs, obj_mask, disp, mpi_all_src, disparity
     flow_mix, frame_mix, fill_mask, _ = render_sample_pair(
         src_imgs, obj_mask, mpi_all_src, disparity_all_src, k_src, k_tgt, cam_ext, cam_ext_dynamic, hard_flow,
         mask_thresh)
-    flow_mix, frame_mix, fill_mask = flow_mix.cpu().numpy(), frame_mix.cpu().numpy(), fill_mask.cpu().numpy()
-    inpainted = cv2.inpaint(frame_mix, fill_mask, 3, cv2.INPAINT_NS)                        # :284-286
-    return flow_mix, src_np, inpainted, None
+    inpainted = inpaint_ns(frame_mix, fill_mask, 3)                                         # :284-286, on the device
+    return flow_mix.cpu().numpy(), src_np, inpainted.cpu().numpy(), None
