@@ -6,14 +6,18 @@
 // from the eikonal update, is inpainted AT ONCE from all non-hole pixels within the radius, and enters the queue.  A
 // filled pixel is a source for every later one, so the result is defined by that global order (oracle/inpaint_oracle.c
 // restates it and is pinned against cv2.inpaint).  What can run in parallel without changing a bit:
-//   * images: one warp marches one image (a launch takes a batch: the generator's samples are independent);
+//   * images: a launch takes a batch (the generator's samples are independent);
+//   * separate holes of one image: a filled pixel is read by later ones only within radius + 1 of it (window plus
+//     gradient stencil), so hole pixels at least radius + 2 columns (or rows) apart never see each other's results.
+//     inpaint_init_kernel cuts the image at hole-free runs of columns, then each column segment at hole-free runs of
+//     rows, into up to MAXSEG rectangles; one warp marches each rectangle with its own queue;
 //   * the window of one pixel: its (2r+1)^2 positions x 3 colours (flags, two gradient stencils, weight) go one per
 //     lane; only the two running sums per colour are serial fp32 chains in row-major order, taken by six lanes from
 //     shared memory over the order-preserving compaction of the valid positions;
 //   * the queue: a new arrival time is at least 0.707 later than the pixel that caused it, so with buckets of width
 //     0.5 nothing is ever inserted into the bucket being drained: the warp extracts the next non-empty bucket from the
 //     pending list (stable ballot compaction), sorts it by (t, insertion number) with a bitonic network -- in
-//     registers up to 32 entries, in shared memory up to SORT_SMEM, in global memory beyond -- and pops it in order.
+//     shared memory up to SORT_SMEM entries, in global memory beyond -- and pops it in order.
 // All float steps use the explicit IEEE intrinsics (no contraction); the arithmetic types (float sqrt and quotient in
 // the direction term, double quotient before the final rounding) are cv2's as pinned by the oracle tests.
 #include "common.cuh"
@@ -23,24 +27,59 @@ namespace {
 enum : uint8_t { KNOWN = 0, BAND = 1, INSIDE = 2 };
 constexpr int MAX_RANGE = 5;                     // (2r+1)^2 = 121 window positions at most
 constexpr int MAX_WIN = (2 * MAX_RANGE + 1) * (2 * MAX_RANGE + 1);
-constexpr int SORT_SMEM = 2048;                  // entries sorted in shared memory
+constexpr int SORT_SMEM = 512;                   // entries sorted in shared memory: the kernel's 9.6 KB fit next to the
+                                                 // persistent renderer's 215 KB on the same SM, so it can run under it
+constexpr int MAXC = 16;                         // column segments per image
+constexpr int MAXSEG = 64;                       // rectangles (= marching warps) per image
 constexpr unsigned FULL = 0xffffffffu;
+
+struct Rect {
+    int clo, chi, rlo, rhi;      // inclusive, in the frame-extended image; rlo > rhi: unused slot
+    int offset;                  // its slice of the queue arrays
+    int pad[3];
+};
+
+// Cuts the positions 1..n of an occupancy array at runs of >= gap - 1 free positions (occupied positions at least `gap`
+// apart end up in different segments), at most `maxseg` segments; a segment spans its first occupied position - 1 to
+// its last occupied position + 1 (the band around the hole).  Returns the number of segments.
+__device__ int cut_segments(const uint8_t *occ, int n, int gap, int maxseg, int *lo, int *hi)
+{
+    int ns = 0, last = -(1 << 28);
+    for (int j = 1; j <= n; j++) {
+        if (!occ[j]) continue;
+        if (ns == 0 || (j - last >= gap && ns < maxseg)) lo[ns++] = j - 1;
+        hi[ns - 1] = j + 1;
+        last = j;
+    }
+    return ns;
+}
 
 // One CTA per image.  Flags / arrival times of the image extended by a 1-pixel frame: hole INSIDE, its non-hole
 // 4-neighbours BAND (t = 0), everything else (and the whole frame) KNOWN with t = 1e6 (icvInpaint: cross dilation minus
-// mask, SET_BORDER1); and the initial band as a row-major list (the queue's first bucket, already in pop order):
-// every warp counts the band pixels of its rows, the rows' counts are prefix-summed, every warp compacts its rows.
+// mask, SET_BORDER1); the initial band as one row-major list (every warp counts the band pixels of its rows, the counts
+// are prefix-summed, every warp compacts its rows); and the rectangles that can be marched independently.
 __global__ void __launch_bounds__(1024)
-inpaint_init_kernel(const uint8_t *__restrict__ mask_all, int rows, int cols, uint8_t *__restrict__ f_all,
-                    float *__restrict__ t_all, uint32_t *__restrict__ curp_all, int *__restrict__ nband, size_t cap2)
+inpaint_init_kernel(const uint8_t *__restrict__ mask_all, int rows, int cols, int range, int maxc,
+                    uint8_t *__restrict__ f_all, float *__restrict__ t_all, uint32_t *__restrict__ bandp_all,
+                    int *__restrict__ nband, Rect *__restrict__ rects_all, size_t cap)
 {
-    extern __shared__ int rowcnt[];            // erows + 1
+    extern __shared__ int smi[];
     const int erows = rows + 2, ecols = cols + 2, im = blockIdx.x;
+    int *rowcnt = smi;                                   // erows + 1
+    int *clo = rowcnt + erows + 1, *chi = clo + MAXC;    // column segments
+    int *ncs_p = chi + MAXC;
+    Rect *rect = reinterpret_cast<Rect *>(ncs_p + 4);    // MAXSEG (32-byte records; the ints before keep it 16-byte aligned)
+    uint8_t *colocc = reinterpret_cast<uint8_t *>(rect + MAXSEG);   // ecols
+    uint8_t *colseg = colocc + ecols;                    // ecols
+    uint8_t *rowocc = colseg + ecols;                    // maxc * erows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const uint8_t *m = mask_all + (size_t)im * rows * cols;
     uint8_t *f = f_all + (size_t)im * erows * ecols;
     float *t = t_all + (size_t)im * erows * ecols;
-    uint32_t *curp = curp_all + cap2 * im;
+    uint32_t *bandp = bandp_all + cap * im;
+    for (int j = threadIdx.x; j < ecols; j += blockDim.x) { colocc[j] = 0; colseg[j] = 0; }
+    for (int j = threadIdx.x; j < maxc * erows; j += blockDim.x) rowocc[j] = 0;
+    __syncthreads();
     auto hole = [&](int y, int x) { return y >= 1 && x >= 1 && y <= rows && x <= cols && m[(y - 1) * cols + (x - 1)] != 0; };
     for (int i = warp; i < erows; i += nwarps) {
         int cnt = 0;
@@ -50,7 +89,7 @@ inpaint_init_kernel(const uint8_t *__restrict__ mask_all, int rows, int cols, ui
             if (j < ecols) {
                 uint8_t fv = KNOWN;
                 float tv = 1.0e6f;
-                if (hole(i, j)) fv = INSIDE;
+                if (hole(i, j)) { fv = INSIDE; colocc[j] = 1; }
                 else if (i > 0 && j > 0 && i < erows - 1 && j < ecols - 1 &&
                          (hole(i - 1, j) || hole(i + 1, j) || hole(i, j - 1) || hole(i, j + 1))) {
                     fv = BAND; tv = 0.f; band = true;
@@ -78,19 +117,47 @@ inpaint_init_kernel(const uint8_t *__restrict__ mask_all, int rows, int cols, ui
             carry += __shfl_sync(FULL, inc, 31);
         }
         if (lane == 0) nband[im] = carry;
+    } else if (threadIdx.x == 32) {   // column segments
+        const int ncs = cut_segments(colocc, cols, range + 2, maxc, clo, chi);
+        *ncs_p = ncs;
+        for (int c = 0; c < ncs; c++)
+            for (int j = clo[c]; j <= chi[c]; j++) colseg[j] = (uint8_t)c;
     }
     __syncthreads();
+    const int ncs = *ncs_p;
     const unsigned lt = (1u << lane) - 1u;
     for (int i = warp; i < erows; i += nwarps) {
         int at = rowcnt[i];
         for (int j0 = 0; j0 < ecols; j0 += 32) {
             const int j = j0 + lane;
-            const bool band = j < ecols && f[i * ecols + j] == BAND;
-            const unsigned b = __ballot_sync(FULL, band);
-            if (band) curp[at + __popc(b & lt)] = (uint32_t)(i * ecols + j);
+            const uint8_t fv = j < ecols ? f[i * ecols + j] : (uint8_t)KNOWN;
+            if (fv == INSIDE) rowocc[colseg[j] * erows + i] = 1;
+            const unsigned b = __ballot_sync(FULL, fv == BAND);
+            if (fv == BAND) bandp[at + __popc(b & lt)] = (uint32_t)(i * ecols + j);
             at += __popc(b);
         }
     }
+    __syncthreads();
+    // rows of every column segment -> rectangles in fixed slots: segment c owns slots c * per .. c * per + per - 1
+    const int per = ncs > 0 ? MAXSEG / ncs : MAXSEG;
+    if ((int)threadIdx.x < MAXSEG) rect[threadIdx.x] = Rect{0, 0, 1, 0, 0, {0, 0, 0}};
+    __syncthreads();
+    if ((int)threadIdx.x < ncs) {
+        const int c = threadIdx.x;
+        int rlo[MAXSEG], rhi[MAXSEG];
+        const int nr = cut_segments(rowocc + c * erows, rows, range + 2, per, rlo, rhi);
+        for (int r = 0; r < nr; r++) rect[c * per + r] = Rect{clo[c], chi[c], rlo[r], rhi[r], 0, {0, 0, 0}};
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int r = 0; r < MAXSEG; r++) {
+            rect[r].offset = off;
+            if (rect[r].rlo <= rect[r].rhi) off += (rect[r].chi - rect[r].clo + 1) * (rect[r].rhi - rect[r].rlo + 1);
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < MAXSEG) rects_all[(size_t)im * MAXSEG + threadIdx.x] = rect[threadIdx.x];
 }
 
 // FastMarching_solve: eikonal update of a pixel from two of its 4-neighbours, in double like OpenCV
@@ -109,20 +176,21 @@ __device__ __forceinline__ float fmm_solve(int p1, int p2, const uint8_t *f, con
     return (float)sol;
 }
 
-// ascending bitonic sort of n = 2^k (key, pos) pairs held in `keys` / `pos` (shared or global memory), one warp
+// ascending bitonic sort of n (key, pos) pairs in shared or global memory by one warp.  Every merge runs in ascending
+// direction (first step against the mirrored partner), so the padding up to the next power of two is virtual: a
+// partner beyond n counts as +infinity and is never touched.
 __device__ void bitonic_sort(unsigned long long *keys, uint32_t *pos, int n, int lane)
 {
-    for (int k = 2; k <= n; k <<= 1)
+    for (int k = 2; (k >> 1) < n; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = lane; i < n; i += 32) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) {
-                        keys[i] = b; keys[ixj] = a;
+                const int partner = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+                if (partner > i && partner < n) {
+                    const unsigned long long a = keys[i], b = keys[partner];
+                    if (a > b) {
+                        keys[i] = b; keys[partner] = a;
                         const uint32_t pa = pos[i];
-                        pos[i] = pos[ixj]; pos[ixj] = pa;
+                        pos[i] = pos[partner]; pos[partner] = pa;
                     }
                 }
             }
@@ -138,14 +206,26 @@ struct MarchSmem {
     uint32_t spos[SORT_SMEM];
 };
 
-// One warp per image.  cur_* / pend_* : per image capacity `cap2` (a power of two >= rows * cols).
+// weight of one window pixel for one colour (icvNSInpaintFMM): gx / gy the two gradient sums, dst = 1 / (|r|^4 + 1)
+__device__ __forceinline__ float ns_weight(float gx, float gy, float rx, float ry, float rl, float dst)
+{
+    gx = -gx;
+    float dir = __fadd_rn(__fmul_rn(rx, gx), __fmul_rn(ry, gy));
+    if (fabs((double)dir) <= 0.01) dir = 0.000001f;
+    else dir = fabsf(__fdiv_rn(dir, __fsqrt_rn(__fmul_rn(rl, __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy))))));
+    return __fmul_rn(dst, dir);
+}
+
+// One warp per (rectangle, image).
 __global__ void __launch_bounds__(32)
 inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_all, uint8_t *out_all,
                         unsigned long long *curk_all, uint32_t *curp_all, unsigned long long *pendk_all,
-                        uint32_t *pendp_all, const int *nband, size_t cap2)
+                        uint32_t *pendp_all, const uint32_t *bandp_all, const int *nband, const Rect *rects_all, size_t cap)
 {
     __shared__ MarchSmem sm;
-    const int lane = threadIdx.x, im = blockIdx.x;
+    const int lane = threadIdx.x, im = blockIdx.y;
+    const Rect rc = rects_all[(size_t)im * MAXSEG + blockIdx.x];
+    if (rc.rlo > rc.rhi) return;
     const int erows = rows + 2, ecols = cols + 2;
     const size_t per = (size_t)erows * ecols;
     // The warp re-reads what one of its lanes wrote a moment ago.  Plain accesses (L1 hits) are enough: every write is
@@ -153,8 +233,9 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
     uint8_t *f = f_all + per * im;
     float *t = t_all + per * im;
     uint8_t *out = out_all + (size_t)im * rows * cols * 3;
-    unsigned long long *curk = curk_all + cap2 * im, *pendk = pendk_all + cap2 * im;
-    uint32_t *curp = curp_all + cap2 * im, *pendp = pendp_all + cap2 * im;
+    unsigned long long *curk = curk_all + cap * im + rc.offset, *pendk = pendk_all + cap * im + rc.offset;
+    uint32_t *curp = curp_all + cap * im + rc.offset, *pendp = pendp_all + cap * im + rc.offset;
+    const uint32_t *bandp = bandp_all + cap * im;
     const unsigned lt = (1u << lane) - 1u;
     const int win = 2 * range + 1;
 
@@ -168,9 +249,25 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
         if (in) sm.off[nwin + __popc(b & lt)] = (dk << 16) | (dl & 0xffff);
         nwin += __popc(b);
     }
+    // ---- the rectangle's part of the initial band (row-major, t = 0): bucket 0, in pop order already ----
+    int nc = 0;
+    {
+        const int nb = nband[im];
+        for (int base = 0; base < nb; base += 32) {
+            const int e = base + lane;
+            uint32_t pos = 0;
+            bool in = false;
+            if (e < nb) {
+                pos = bandp[e];
+                const int i = pos / ecols, j = pos - i * ecols;
+                in = i >= rc.rlo && i <= rc.rhi && j >= rc.clo && j <= rc.chi;
+            }
+            const unsigned b = __ballot_sync(FULL, in);
+            if (in) curp[nc + __popc(b & lt)] = pos;
+            nc += __popc(b);
+        }
+    }
     __syncwarp();
-    // ---- initial band, row-major, t = 0 (inpaint_init_kernel): bucket 0, in pop order already ----
-    int nc = nband[im];
     uint32_t seq = (uint32_t)nc;
     int np = 0;
 
@@ -201,42 +298,59 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
                 const float dist = __shfl_sync(FULL, sol, 0);
 
                 // ---- the window: one position per lane, all three colours ----
+                // away from the image border the gradient stencils are the plain 4-neighbours of the window pixel
+                const bool interior = i - range >= 2 && i + range <= erows - 3 && j - range >= 2 && j + range <= ecols - 3;
                 int nvalid = 0;
                 for (int base = 0; base < nwin; base += 32) {
                     const int p = base + lane;
                     const int od = sm.off[p < nwin ? p : 0], dk = od >> 16, dl = (int)(short)(od & 0xffff);
-                    const int k = i + dk, l = j + dl;
-                    bool valid = p < nwin && k > 0 && l > 0 && k < erows - 1 && l < ecols - 1;
-                    if (valid) valid = f[k * ecols + l] != INSIDE;
+                    const int k = i + dk, l = j + dl, kl = k * ecols + l;
+                    bool valid = p < nwin && (interior || (k > 0 && l > 0 && k < erows - 1 && l < ecols - 1));
+                    if (valid) valid = f[kl] != INSIDE;
                     float wv[3] = {0.f, 0.f, 0.f}, wiv[3] = {0.f, 0.f, 0.f};
                     if (valid) {
-                        const int km = k - 1 + (k == 1), kp = k - 1 - (k == erows - 2);
-                        const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ecols - 2);
-                        const bool fdn = f[(k + 1) * ecols + l] != INSIDE, fup = f[(k - 1) * ecols + l] != INSIDE;
-                        const bool frt = f[k * ecols + l + 1] != INSIDE, flf = f[k * ecols + l - 1] != INSIDE;
-                        const float ry = (float)(i - k), rx = (float)(j - l);
+                        const bool fdn = f[kl + ecols] != INSIDE, fup = f[kl - ecols] != INSIDE;
+                        const bool frt = f[kl + 1] != INSIDE, flf = f[kl - 1] != INSIDE;
+                        const float ry = (float)(-dk), rx = (float)(-dl);
                         const float rl = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
                         const float dst = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(rl, rl), 1.f));
-                        const int o_a = ((kp + 1) * cols + lm) * 3, o_b = (kp * cols + lm) * 3;
-                        const int o_c = ((km - 1) * cols + lm) * 3, o_d = (km * cols + lp + 1) * 3;
-                        const int o_e = (km * cols + lm) * 3, o_f = (km * cols + lm - 1) * 3;
-                        const int o_v = ((k - 1) * cols + (l - 1)) * 3;
+                        if (interior) {
+                            const uint8_t *c0 = out + ((k - 1) * cols + (l - 1)) * 3;
+                            const int rs = cols * 3;
 #pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const int a = out[o_a + c], b = out[o_b + c], cc = out[o_c + c];
-                            const int d = out[o_d + c], ee = out[o_e + c], ff = out[o_f + c];
-                            float gx, gy;
-                            if (fdn) gx = fup ? (float)(abs(a - b) + abs(b - cc)) : (float)abs(a - b) * 2.0f;
-                            else gx = fup ? (float)abs(b - cc) * 2.0f : 0.f;
-                            if (frt) gy = flf ? (float)(abs(d - ee) + abs(ee - ff)) : (float)abs(d - ee) * 2.0f;
-                            else gy = flf ? (float)abs(ee - ff) * 2.0f : 0.f;
-                            gx = -gx;
-                            float dir = __fadd_rn(__fmul_rn(rx, gx), __fmul_rn(ry, gy));
-                            if (fabs((double)dir) <= 0.01) dir = 0.000001f;
-                            else dir = fabsf(__fdiv_rn(dir, __fsqrt_rn(__fmul_rn(rl, __fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy))))));
-                            const float w = __fmul_rn(dst, dir);
-                            wv[c] = w;
-                            wiv[c] = __fmul_rn(w, (float)(int)out[o_v + c]);
+                            for (int c = 0; c < 3; c++) {
+                                const int ce = c0[c], dn = c0[rs + c], up = c0[c - rs], rt = c0[3 + c], lf = c0[c - 3];
+                                float gx, gy;
+                                if (fdn) gx = fup ? (float)(abs(dn - ce) + abs(ce - up)) : (float)abs(dn - ce) * 2.0f;
+                                else gx = fup ? (float)abs(ce - up) * 2.0f : 0.f;
+                                if (frt) gy = flf ? (float)(abs(rt - ce) + abs(ce - lf)) : (float)abs(rt - ce) * 2.0f;
+                                else gy = flf ? (float)abs(ce - lf) * 2.0f : 0.f;
+                                const float w = ns_weight(gx, gy, rx, ry, rl, dst);
+                                wv[c] = w;
+                                wiv[c] = __fmul_rn(w, (float)ce);
+                            }
+                        } else {
+                            // at the border OpenCV shifts the stencil rows / columns inwards (km, kp, lm, lp); the value
+                            // itself is read at the pixel
+                            const int km = k - 1 + (k == 1), kp = k - 1 - (k == erows - 2);
+                            const int lm = l - 1 + (l == 1), lp = l - 1 - (l == ecols - 2);
+                            const int o_a = ((kp + 1) * cols + lm) * 3, o_b = (kp * cols + lm) * 3;
+                            const int o_c = ((km - 1) * cols + lm) * 3, o_d = (km * cols + lp + 1) * 3;
+                            const int o_e = (km * cols + lm) * 3, o_f = (km * cols + lm - 1) * 3;
+                            const int o_v = ((k - 1) * cols + (l - 1)) * 3;
+#pragma unroll
+                            for (int c = 0; c < 3; c++) {
+                                const int a = out[o_a + c], b = out[o_b + c], cc = out[o_c + c];
+                                const int d = out[o_d + c], ee = out[o_e + c], ff = out[o_f + c];
+                                float gx, gy;
+                                if (fdn) gx = fup ? (float)(abs(a - b) + abs(b - cc)) : (float)abs(a - b) * 2.0f;
+                                else gx = fup ? (float)abs(b - cc) * 2.0f : 0.f;
+                                if (frt) gy = flf ? (float)(abs(d - ee) + abs(ee - ff)) : (float)abs(d - ee) * 2.0f;
+                                else gy = flf ? (float)abs(ee - ff) * 2.0f : 0.f;
+                                const float w = ns_weight(gx, gy, rx, ry, rl, dst);
+                                wv[c] = w;
+                                wiv[c] = __fmul_rn(w, (float)(int)out[o_v + c]);
+                            }
                         }
                     }
                     const unsigned vb = __ballot_sync(FULL, valid);
@@ -303,20 +417,13 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
         np = nkeep;
         // ---- sort the bucket by (t, insertion number) ----
         if (nc > 1) {
-            int n2 = 1;
-            while (n2 < nc) n2 <<= 1;
-            if (n2 <= SORT_SMEM) {
-                for (int e = lane; e < n2; e += 32) {
-                    sm.skey[e] = e < nc ? curk[e] : ~0ull;
-                    sm.spos[e] = e < nc ? curp[e] : 0u;
-                }
+            if (nc <= SORT_SMEM) {
+                for (int e = lane; e < nc; e += 32) { sm.skey[e] = curk[e]; sm.spos[e] = curp[e]; }
                 __syncwarp();
-                bitonic_sort(sm.skey, sm.spos, n2, lane);
+                bitonic_sort(sm.skey, sm.spos, nc, lane);
                 for (int e = lane; e < nc; e += 32) curp[e] = sm.spos[e];
             } else {
-                for (int e = nc + lane; e < n2; e += 32) { curk[e] = ~0ull; curp[e] = 0u; }
-                __syncwarp();
-                bitonic_sort(curk, curp, n2, lane);
+                bitonic_sort(curk, curp, nc, lane);
             }
             __syncwarp();
         }
@@ -325,49 +432,59 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
 
 }  // namespace
 
-// cap2: power of two >= rows * cols (every pixel enters the queue at most once; the bitonic network pads to 2^k)
-static size_t inpaint_cap2(int rows, int cols)
-{
-    size_t c = 32;
-    while (c < (size_t)rows * cols) c <<= 1;
-    return c;
-}
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// column segments the init kernel can keep row occupancies for in shared memory
+static int inpaint_maxc(int rows)
+{
+    const int m = (150 * 1024) / (rows + 2);
+    return m < 1 ? 1 : m > MAXC ? MAXC : m;
+}
 
 MPIFLOW_API size_t mpiflow_inpaint_ns_workspace_bytes(int n, int rows, int cols)
 {
     if (n <= 0 || rows <= 0 || cols <= 0) return 0;
-    const size_t per = (size_t)(rows + 2) * (cols + 2), cap2 = inpaint_cap2(rows, cols);
-    return align256(per * n) + align256(per * n * 4) + 2 * align256(cap2 * n * 8) + 2 * align256(cap2 * n * 4) +
-           align256((size_t)n * sizeof(int));
+    const size_t per = (size_t)(rows + 2) * (cols + 2);      // every pixel enters a queue at most once
+    return align256(per * n) + align256(per * n * 4) + 2 * align256(per * n * 8) + 3 * align256(per * n * 4) +
+           align256((size_t)n * sizeof(int)) + align256((size_t)n * MAXSEG * sizeof(Rect));
 }
 
 MPIFLOW_API int mpiflow_inpaint_ns_u8(const uint8_t *img, const uint8_t *mask, int n, int rows, int cols, int radius,
                                       uint8_t *out, void *workspace, size_t workspace_bytes, void *stream)
 {
     MF_CHECK_ARG(img && mask && out && workspace);
-    MF_CHECK_ARG(n > 0 && rows > 0 && cols > 0 && (int64_t)(rows + 2) * (cols + 2) * 3 < (1ll << 31) && rows + 3 <= 12000);
+    MF_CHECK_ARG(n > 0 && n <= 65535 && rows > 0 && cols > 0 && (int64_t)(rows + 2) * (cols + 2) * 3 < (1ll << 31));
+    MF_CHECK_ARG(rows <= 16000 && cols <= 16000);
     MF_CHECK_ARG(((uintptr_t)workspace & 255) == 0);
     int range = radius < 1 ? 1 : radius;        // icvInpaint: range = cvRound(radius) clamped to [1, 100]
     MF_CHECK_ARG(range <= MAX_RANGE);
     if (workspace_bytes < mpiflow_inpaint_ns_workspace_bytes(n, rows, cols)) return MPIFLOW_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t per = (size_t)(rows + 2) * (cols + 2), cap2 = inpaint_cap2(rows, cols);
+    const size_t per = (size_t)(rows + 2) * (cols + 2);
     char *w = reinterpret_cast<char *>(workspace);
     uint8_t *f = reinterpret_cast<uint8_t *>(w); w += align256(per * n);
     float *t = reinterpret_cast<float *>(w); w += align256(per * n * 4);
-    unsigned long long *curk = reinterpret_cast<unsigned long long *>(w); w += align256(cap2 * n * 8);
-    unsigned long long *pendk = reinterpret_cast<unsigned long long *>(w); w += align256(cap2 * n * 8);
-    uint32_t *curp = reinterpret_cast<uint32_t *>(w); w += align256(cap2 * n * 4);
-    uint32_t *pendp = reinterpret_cast<uint32_t *>(w); w += align256(cap2 * n * 4);
-    int *nband = reinterpret_cast<int *>(w);
+    unsigned long long *curk = reinterpret_cast<unsigned long long *>(w); w += align256(per * n * 8);
+    unsigned long long *pendk = reinterpret_cast<unsigned long long *>(w); w += align256(per * n * 8);
+    uint32_t *curp = reinterpret_cast<uint32_t *>(w); w += align256(per * n * 4);
+    uint32_t *pendp = reinterpret_cast<uint32_t *>(w); w += align256(per * n * 4);
+    uint32_t *bandp = reinterpret_cast<uint32_t *>(w); w += align256(per * n * 4);
+    int *nband = reinterpret_cast<int *>(w); w += align256((size_t)n * sizeof(int));
+    Rect *rects = reinterpret_cast<Rect *>(w);
     if (out != img) {
         cudaError_t e = cudaMemcpyAsync(out, img, (size_t)n * rows * cols * 3, cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return (int)e;
     }
-    inpaint_init_kernel<<<n, 1024, (rows + 3) * sizeof(int), st>>>(mask, rows, cols, f, t, curp, nband, cap2);
+    const int maxc = inpaint_maxc(rows);
+    const size_t smem = (size_t)(rows + 3 + 2 * MAXC + 4) * sizeof(int) + MAXSEG * sizeof(Rect) + 2 * (size_t)(cols + 2) +
+                        (size_t)maxc * (rows + 2);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(inpaint_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    inpaint_init_kernel<<<n, 1024, smem, st>>>(mask, rows, cols, range, maxc, f, t, bandp, nband, rects, per);
     int rc = mf_launch_status();
     if (rc) return rc;
-    inpaint_ns_march_kernel<<<n, 32, 0, st>>>(rows, cols, range, f, t, out, curk, curp, pendk, pendp, nband, cap2);
+    inpaint_ns_march_kernel<<<dim3(MAXSEG, n), 32, 0, st>>>(rows, cols, range, f, t, out, curk, curp, pendk, pendp, bandp,
+                                                          nband, rects, per);
     return mf_launch_status();
 }

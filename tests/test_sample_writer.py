@@ -53,3 +53,18 @@ def test_device_tensors_are_copied_on_a_side_stream(gold, tmp_path):
             torch.empty(1 << 20, device="cuda").fill_(k)      # allocator churn while copies are in flight
     for k in range(6):
         _check_files(str(tmp_path), f"demo_{k}", gold)
+
+
+@pytest.mark.gpu
+def test_device_inpaint_gives_the_same_files(gold, tmp_path):
+    """hole filling on the GPU (batches of 4, a partial batch at the end): the files still equal the reference's"""
+    from sample_writer import SampleWriter
+    dev = lambda k: torch.from_numpy(gold[k]).cuda()
+    with SampleWriter(str(tmp_path), workers=2, depth=2, device_inpaint=True, inpaint_batch=4) as w:
+        for k in range(10):
+            flow, frame, fill = dev("flow_mix"), dev("frame_mix"), dev("fill_mask")
+            w.submit(f"demo_{k}", flow, frame, fill, gold["src_np"])
+            frame.fill_(0)                                    # the caller may reuse its buffers at once
+            del flow, frame, fill
+    for k in range(10):
+        _check_files(str(tmp_path), f"demo_{k}", gold)

@@ -2,7 +2,9 @@
 without the AdaMPI network).  Prints one JSON line: samples/s of the device part alone and of the whole loop including
 hole filling and file writing by the writer's worker threads.
 
-    python tools/generate_samples.py [n_samples [workers [out_dir]]]
+    python tools/generate_samples.py [n_samples [workers [out_dir [device_inpaint_batch]]]]
+
+device_inpaint_batch > 0: the holes are filled on the GPU in batches of that many samples (SampleWriter(device_inpaint=True)).
 """
 import json
 import os
@@ -25,6 +27,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     workers = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     out_dir = sys.argv[3] if len(sys.argv) > 3 else tempfile.mkdtemp(prefix="mpiflow_samples_")
+    dev_batch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     S, H, W = 64, 384, 1280
     R.CHECK_SINGULAR = False
     T = lambda a: torch.from_numpy(a).cuda()
@@ -59,7 +62,7 @@ def main():
     t_dev = time.perf_counter() - t0
 
     t0 = time.perf_counter()
-    with SampleWriter(out_dir, workers=workers, depth=2 * workers) as w:
+    with SampleWriter(out_dir, workers=workers, depth=2 * workers, device_inpaint=dev_batch > 0, inpaint_batch=max(dev_batch, 1)) as w:
         for k in range(n):
             flow_mix, frame_mix, fill = device_part(k)
             w.submit(f"demo_{k}", flow_mix, frame_mix, fill, src_np)
@@ -71,7 +74,7 @@ def main():
                for f in os.listdir(os.path.join(out_dir, d)))
     print(json.dumps({"samples": n, "workers": workers, "device_only_samples_per_s": n / t_dev,
                       "submit_loop_samples_per_s": n / t_submit, "with_fill_and_files_samples_per_s": n / t_all,
-                      "hole_fraction_last_sample": holes, "bytes_written": size, "out_dir": out_dir}))
+                      "hole_fraction_last_sample": holes, "device_inpaint_batch": dev_batch, "bytes_written": size, "out_dir": out_dir}))
 
 
 if __name__ == "__main__":
