@@ -12,14 +12,22 @@
 // are marked independently, the last winner per target is an atomicMax over sorted positions.
 // Everything is integer except the single fp32 '<', so the result is deterministic.
 //
-// ONE launch: the phases (keys + histogram, per pass a scan of the histograms and a stable scatter, resolve, colours)
+// Default path ("chains", round 2): real index maps send one, rarely a handful of source pixels to a target, so the sort
+// is overkill.  splat_chain_build_kernel threads every source pixel onto a per-target list with one atomicExch
+// (arbitrary order); splat_chain_resolve_kernel, one thread per target, pulls the list (up to CHAIN_MAX writers) into
+// registers, orders it by raster index with an insertion sort and evaluates the closed form.  A target with more
+// writers raises a flag, and the radix path below -- launched behind it, every kernel gated on that flag -- redoes the
+// whole call (it writes the same bytes for the targets already resolved).  memset + 2 kernels + 1 gated launch.
+//
+// Radix path: the phases (keys + histogram, per pass a scan of the histograms and a stable scatter, resolve, colours)
 // are device functions over "virtual blocks"; splat_fused_kernel is launched cooperatively with as many CTAs as are
-// co-resident and walks them phase by phase with grid-wide barriers (at 1280x384 the seven launches of the unfused
-// form were launch-latency bound: 64 us of which ~10 us were work).  MPIFLOW_SPLAT_FUSED=0 keeps one launch per phase.
+// co-resident and walks them phase by phase with grid-wide barriers; when a cooperative launch is not possible (stream
+// capture) every phase is its own launch.
 #include <cooperative_groups.h>
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -212,13 +220,17 @@ __device__ __forceinline__ void splat_rgb(uint32_t t, const uint32_t *__restrict
 __global__ void __launch_bounds__(SORT_THREADS)
 splat_keys_hist_kernel(const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h, int w, uint32_t n,
                        int digit_bits, uint32_t nblocks, uint32_t *__restrict__ keys, uint32_t *__restrict__ winpos,
-                       uint32_t *__restrict__ hist0, uint32_t *__restrict__ hist_later, uint32_t hist_later_count)
+                       uint32_t *__restrict__ hist0, uint32_t *__restrict__ hist_later, uint32_t hist_later_count,
+                       const uint32_t *gate)
 {
+    if (gate && *gate == 0) return;      // the chain path resolved every target: nothing to redo
     splat_keys_hist(blockIdx.x, gridDim.x, idx, idy, h, w, n, digit_bits, nblocks, keys, winpos, hist0, hist_later, hist_later_count);
 }
 __global__ void __launch_bounds__(SORT_THREADS)
-radix_offsets_kernel(uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t radix, uint32_t *__restrict__ totals)
+radix_offsets_kernel(uint32_t *__restrict__ hist, uint32_t nblocks, uint32_t radix, uint32_t *__restrict__ totals,
+                     const uint32_t *gate)
 {
+    if (gate && *gate == 0) return;
     radix_offsets(blockIdx.x, hist, nblocks, radix, totals);
 }
 template <bool FIRST>
@@ -227,21 +239,100 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
                      int shift, int digit_bits, uint32_t nblocks, const uint32_t *__restrict__ offsets,
                      const uint32_t *__restrict__ totals, uint32_t *__restrict__ keys_out,
                      uint32_t *__restrict__ vals_out, uint32_t *__restrict__ hist_next, int next_shift,
-                     int next_bits)
+                     int next_bits, const uint32_t *gate)
 {
+    if (gate && *gate == 0) return;
     radix_scatter<FIRST>(blockIdx.x, keys_in, vals_in, n, shift, digit_bits, nblocks, offsets, totals, keys_out, vals_out,
                          hist_next, next_shift, next_bits);
 }
 __global__ void splat_resolve_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                      const float *__restrict__ z, uint32_t n, uint32_t *__restrict__ winpos,
-                                     uint8_t *__restrict__ warped)
+                                     uint8_t *__restrict__ warped, const uint32_t *gate)
 {
+    if (gate && *gate == 0) return;
     splat_resolve(blockIdx.x * blockDim.x + threadIdx.x, keys, vals, z, n, winpos, warped);
 }
 __global__ void splat_rgb_kernel(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ winpos,
-                                 const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ warped)
+                                 const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ warped,
+                                 const uint32_t *gate)
 {
+    if (gate && *gate == 0) return;
     splat_rgb(blockIdx.x * blockDim.x + threadIdx.x, vals, winpos, src, n, warped);
+}
+
+// ---- chain path -------------------------------------------------------------------------------------------------
+constexpr int MF_MAX_DEVICES_SPLAT = 64;
+constexpr int CHAIN_MAX = 16;     // writers per target resolved in registers / local memory
+
+// head[t] = -1 (memset) ; every source pixel k: next[k] = exchange(head[target(k)], k).  Thread 0 clears the overflow flag.
+__global__ void __launch_bounds__(256)
+splat_chain_build_kernel(const int64_t *__restrict__ idx, const int64_t *__restrict__ idy, int h, int w, uint32_t n,
+                         int *__restrict__ head, int *__restrict__ next, uint32_t *__restrict__ overflow)
+{
+    const uint32_t k = blockIdx.x * 256u + threadIdx.x;
+    if (k == 0) *overflow = 0;
+    if (k >= n) return;
+    const int x = (int)idx[k], y = (int)idy[k];               // narrowed through int exactly like warping.c:16-17
+    if (x < 0 || x >= w || y < 0 || y >= h) return;           // out-of-range target: dropped (as the radix path does)
+    next[k] = atomicExch(&head[(uint32_t)y * (uint32_t)w + (uint32_t)x], (int)k);
+}
+
+// one thread per target: its writers in raster order, then the serial loop's closed form (see the top of the file).
+// A full block's 256 five-byte records are 320 aligned words: they are read, patched in shared memory and written
+// back as words (bytes no writer touches keep the caller's content either way).
+__global__ void __launch_bounds__(256)
+splat_chain_resolve_kernel(const int *__restrict__ head, const int *__restrict__ next, const float *__restrict__ z,
+                           const uint8_t *__restrict__ src, uint32_t n, uint8_t *__restrict__ warped,
+                           uint32_t *__restrict__ overflow, int words_ok)
+{
+    __shared__ uint32_t stage[320];
+    const uint32_t t0 = blockIdx.x * 256u, t = t0 + threadIdx.x;
+    const bool staged = words_ok && t0 + 256u <= n;            // block-uniform
+    uint32_t *gw = reinterpret_cast<uint32_t *>(warped + (size_t)t0 * 5);
+    if (staged) {
+        stage[threadIdx.x] = gw[threadIdx.x];
+        if (threadIdx.x < 64) stage[256 + threadIdx.x] = gw[256 + threadIdx.x];
+        __syncthreads();
+    }
+    int k = t < n ? head[t] : -1;
+    int win = -1;
+    float zprev = 1000.f;                                      // dlut[t] when the LAST writer arrives (:8-11, :28)
+    bool touched = k >= 0;
+    if (touched) {
+        const int k2 = next[k];
+        if (k2 < 0) {                                          // one writer: the common case
+            if (z[k] < 1000.f) win = k;
+        } else {
+            int ks[CHAIN_MAX];
+            int cnt = 0;
+            for (int c = k; c >= 0; c = next[c]) {
+                if (cnt == CHAIN_MAX) { *overflow = 1; touched = false; break; }   // left to the radix path
+                int j = cnt++;                                 // insertion sort by raster index
+                while (j > 0 && ks[j - 1] > c) { ks[j] = ks[j - 1]; j--; }
+                ks[j] = c;
+            }
+            if (touched)
+                for (int i = 0; i < cnt; i++) {
+                    const float zi = z[ks[i]];
+                    if (zi < zprev) win = ks[i];               // :19-21 (for the last writer zprev is its dlut)
+                    if (i + 1 < cnt) zprev = zi;               // :28 unconditionally
+                }
+        }
+    }
+    uint8_t *o = staged ? reinterpret_cast<uint8_t *>(stage) + threadIdx.x * 5 : warped + (size_t)t * 5;
+    if (touched) {
+        if (win >= 0) {
+            const uint8_t *s = src + (size_t)win * 3;
+            o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+        }
+        o[3] = 1;                                              // :23
+        o[4] = (zprev != 1000.f) ? 0 : 1;                      // :24-27
+    }
+    if (staged) {
+        __syncthreads();
+        gw[threadIdx.x] = stage[threadIdx.x];
+        if (threadIdx.x < 64) gw[256 + threadIdx.x] = stage[256 + threadIdx.x];
+    }
 }
 
 // ---- all phases in one cooperative launch ----
@@ -249,6 +340,7 @@ struct SplatArgs {
     const uint8_t *src; const int64_t *idx, *idy; const float *z; uint8_t *warped;
     int h, w; uint32_t n, nblocks; int passes, digit_bits; size_t hist_stride;
     uint32_t *kA, *vA, *kB, *vB, *winpos, *hist, *totals;
+    const uint32_t *gate;      // non-null: run only if *gate != 0 (uniform over the grid)
 };
 
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -256,6 +348,7 @@ splat_fused_kernel(const SplatArgs a)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
+    if (a.gate && *a.gate == 0) return;
     const uint32_t radix = 1u << a.digit_bits;
     for (uint32_t vb = blockIdx.x; vb < a.nblocks; vb += gridDim.x) {
         splat_keys_hist(vb, a.nblocks, a.idx, a.idy, a.h, a.w, a.n, a.digit_bits, a.nblocks, a.kA, a.winpos, a.hist,
@@ -293,7 +386,7 @@ splat_fused_kernel(const SplatArgs a)
 inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct SplatLayout {
-    size_t keysA, valsA, keysB, valsB, winpos, hist, totals, total;
+    size_t keysA, valsA, keysB, valsB, winpos, hist, totals, flag, total;
     uint32_t nblocks;
     int passes, digit_bits;
     size_t hist_stride;   // uint32 per pass
@@ -314,6 +407,7 @@ struct SplatLayout {
         winpos = o; o += al256(n * 4);
         hist = o; o += al256(hist_stride * passes * 4);
         totals = o; o += al256((size_t)MAX_RADIX * 4);
+        flag = o; o += 256;          // chain path: 1 = some target has more than CHAIN_MAX writers
         total = o;
     }
 };
@@ -355,17 +449,41 @@ MPIFLOW_API int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx,
         cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(splat_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     });
+    // chain path first (MPIFLOW_SPLAT_PATH=radix skips it); the radix path behind it runs only if it raised the flag
+    static const bool chain_on = []() { const char *e = getenv("MPIFLOW_SPLAT_PATH"); return !(e && strcmp(e, "radix") == 0); }();
+    uint32_t *gate = nullptr;
+    if (chain_on) {
+        int *head = (int *)kA, *next = (int *)vA;
+        gate = (uint32_t *)(ws + L.flag);
+        cudaError_t e = cudaMemsetAsync(head, 0xff, (size_t)n * 4, st);
+        if (e != cudaSuccess) return (int)e;
+        splat_chain_build_kernel<<<g256, 256, 0, st>>>(idx, idy, h, w, n, head, next, gate);
+        splat_chain_resolve_kernel<<<g256, 256, 0, st>>>(head, next, z, src, n, warped, gate, ((uintptr_t)warped & 3) == 0);
+        int rc = mf_launch_status();
+        if (rc) return rc;
+    }
     static const bool fused_on = []() { const char *e = getenv("MPIFLOW_SPLAT_FUSED"); return !(e && atoi(e) == 0); }();
     if (fused_on) {
-        // as many CTAs as are co-resident (grid-wide barriers between the phases need all of them on the device)
-        int dev = 0, sms = 0, per_sm = 0, coop = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_fused_kernel, SORT_THREADS, scatter_smem) == cudaSuccess &&
-            per_sm > 0) {
-            SplatArgs a{src, idx, idy, z, warped, h, w, n, L.nblocks, L.passes, db, L.hist_stride, kA, vA, kB, vB, winpos, hist, totals};
-            unsigned grid = (unsigned)(sms * per_sm);
+        // as many CTAs as are co-resident (grid-wide barriers between the phases need all of them on the device);
+        // the device queries are cached per device and shared-memory size (they cost microseconds of host time per call)
+        static std::mutex mu;
+        static int cache_grid[MF_MAX_DEVICES_SPLAT][2] = {};
+        static size_t cache_smem[MF_MAX_DEVICES_SPLAT] = {};
+        int dev = 0, sms = 0, per_sm = 0, coop = 0, full_grid = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < MF_MAX_DEVICES_SPLAT) {
+            std::lock_guard<std::mutex> lock(mu);
+            if (cache_grid[dev][0] && cache_smem[dev] == scatter_smem) full_grid = cache_grid[dev][1];
+            else if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_fused_kernel, SORT_THREADS, scatter_smem) == cudaSuccess &&
+                     per_sm > 0) {
+                full_grid = sms * per_sm;
+                cache_grid[dev][0] = 1; cache_grid[dev][1] = full_grid; cache_smem[dev] = scatter_smem;
+            }
+        }
+        if (full_grid > 0) {
+            SplatArgs a{src, idx, idy, z, warped, h, w, n, L.nblocks, L.passes, db, L.hist_stride, kA, vA, kB, vB, winpos, hist, totals, gate};
+            unsigned grid = (unsigned)full_grid;
             if (grid > L.nblocks) grid = L.nblocks;
             void *args[] = {&a};
             cudaError_t e = cudaLaunchCooperativeKernel((void *)splat_fused_kernel, dim3(grid), dim3(SORT_THREADS), args,
@@ -376,23 +494,23 @@ MPIFLOW_API int mpiflow_forward_warp_f32(const uint8_t *src, const int64_t *idx,
     }
     splat_keys_hist_kernel<<<L.nblocks, SORT_THREADS, radix * sizeof(uint32_t), st>>>(
         idx, idy, h, w, n, db, L.nblocks, kA, winpos, hist, hist + L.hist_stride,
-        (uint32_t)(L.hist_stride * (L.passes - 1)));
+        (uint32_t)(L.hist_stride * (L.passes - 1)), gate);
     for (int p = 0; p < L.passes; p++) {
         uint32_t *hp = hist + (size_t)p * L.hist_stride;
         const bool more = p + 1 < L.passes;
-        radix_offsets_kernel<<<(radix + SORT_WARPS - 1) / SORT_WARPS, SORT_THREADS, 0, st>>>(hp, L.nblocks, radix, totals);
+        radix_offsets_kernel<<<(radix + SORT_WARPS - 1) / SORT_WARPS, SORT_THREADS, 0, st>>>(hp, L.nblocks, radix, totals, gate);
         if (p == 0)
             radix_scatter_kernel<true><<<L.nblocks, SORT_THREADS, scatter_smem, st>>>(
-                kA, nullptr, n, 0, db, L.nblocks, hp, totals, kB, vB, more ? hp + L.hist_stride : nullptr, db, db);
+                kA, nullptr, n, 0, db, L.nblocks, hp, totals, kB, vB, more ? hp + L.hist_stride : nullptr, db, db, gate);
         else
             radix_scatter_kernel<false><<<L.nblocks, SORT_THREADS, scatter_smem, st>>>(
                 kA, vA, n, p * db, db, L.nblocks, hp, totals, kB, vB, more ? hp + L.hist_stride : nullptr,
-                (p + 1) * db, db);
+                (p + 1) * db, db, gate);
         uint32_t *t = kA; kA = kB; kB = t;
         t = vA; vA = vB; vB = t;
     }
-    splat_resolve_kernel<<<g256, 256, 0, st>>>(kA, vA, z, n, winpos, warped);
-    splat_rgb_kernel<<<g256, 256, 0, st>>>(vA, winpos, src, n, warped);
+    splat_resolve_kernel<<<g256, 256, 0, st>>>(kA, vA, z, n, winpos, warped, gate);
+    splat_rgb_kernel<<<g256, 256, 0, st>>>(vA, winpos, src, n, warped, gate);
     return mf_launch_status();
 }
 

@@ -57,6 +57,42 @@ def test_device_splat_matches_oracle_at_full_sizes(h, w, mode, seed):
     np.testing.assert_array_equal(splat_device(src, idx, idy, z), want)
 
 
+@pytest.mark.parametrize("per", [2, 5, 15, 16, 17, 40])
+def test_exactly_n_writers_per_target(per):
+    """the chain path orders up to 16 writers of a target in registers and hands the call to the radix path beyond:
+    both sides of that boundary, writers scattered over the raster (not adjacent), z with ties and 1000.0"""
+    h, w = 48, 80
+    src, _, _, z = synth.splat_inputs(h, w, 50 + per, "identity")
+    rng = np.random.default_rng(per)
+    tgt = rng.permutation(h * w) // per                      # every used target gets `per` writers (the last one fewer)
+    idx, idy = (tgt % w).reshape(h, w).astype(np.int64), (tgt // w).reshape(h, w).astype(np.int64)
+    np.testing.assert_array_equal(splat_device(src, idx, idy, z), orc.forward_warping(src, idx, idy, z))
+
+
+def test_out_of_range_targets_are_dropped():
+    """the reference would write out of bounds (undefined); both device paths drop such sources"""
+    h, w = 24, 40
+    src, idx, idy, z = synth.splat_inputs(h, w, 61, "dense")
+    bad = np.random.default_rng(3).random((h, w)) < 0.1
+    idx2, idy2 = idx.copy(), idy.copy()
+    idx2[bad] = w + 5
+    keep = ~bad
+    want = np.zeros((h, w, 5), np.uint8)
+    # the oracle on the kept sources only, in raster order: emulate by sending dropped sources nowhere
+    dl = np.full((h, w), 1000.0, np.float32)
+    for i in range(h):
+        for j in range(w):
+            if not keep[i, j]:
+                continue
+            x, y = int(idx[i, j]), int(idy[i, j])
+            if z[i, j] < dl[y, x]:
+                want[y, x, :3] = src[i, j]
+            want[y, x, 3] = 1
+            want[y, x, 4] = 0 if dl[y, x] != 1000.0 else 1
+            dl[y, x] = z[i, j]
+    np.testing.assert_array_equal(splat_device(src, idx2, idy2, z), want)
+
+
 def test_untouched_bytes_keep_caller_content():
     h, w = 20, 30
     src, idx, idy, z = synth.splat_inputs(h, w, 31, "pile")
