@@ -34,6 +34,12 @@ extern "C" {
 /* render flags (keyword arguments of mpi_rendering.render_tgt_rgb_depth, mpi_rendering.py:259-272) */
 #define MPIFLOW_BG_DEPTH_INF 1u /* is_bg_depth_inf */
 #define MPIFLOW_HARD_FLOW 2u    /* hard_flow */
+/* The caller promises that nobody else writes to `workspace` between calls (a workspace owned by one loop, as the
+ * generator's): the plane-spacing table of the previous call is then reused whenever K_src^-1 of entry 0, the
+ * disparities, S, H and W are bit for bit what they were (checked on the device against a key stored behind the table;
+ * no host sync), and launches of fewer than 4 frames use the table too.  Needs mpiflow_render_workspace_bytes_hw.
+ * Zero a workspace once before its first call with this flag (recycled memory may hold the key of an earlier table). */
+#define MPIFLOW_KEEP_TABLE 4u
 /* n consecutive frames of the batch render the same MPI under n poses (utils/utils.py:210-238 renders every sample
  * twice): rgb / sigma then hold B/n MPIs, rgb_sb / sig_sb step between MPIs, everything else stays per frame.
  * n = 1..256, B % n == 0.  (A batch stride of 0 says the same for "all B frames share one MPI".) */
@@ -71,8 +77,9 @@ int mpiflow_plane_homographies_f32(const float *G, const float *Kinv, const floa
  *   out_rgb [B,3,H,W], out_depth [B,1,H,W], out_mask [B,1,H,W] (count of valid planes, :347),
  *   out_flow [B,2,H,W] (flowA2B, source frame), out_obj [B,1,H,W]      -- all dense
  *   workspace: mpiflow_render_workspace_bytes(B, S) bytes, device, 16-byte aligned; with
- *     mpiflow_render_workspace_bytes_hw(B, S, H, W) bytes (S*H*W floats more) launches of 4 or more frames whose
+ *     mpiflow_render_workspace_bytes_hw(B, S, H, W) bytes (S*H*W floats and a key more) launches of 4 or more frames whose
  *     K_src^-1 and disparities agree evaluate the source-frame plane spacing once per launch instead of per frame
+ *     (MPIFLOW_KEEP_TABLE: once per workspace, and for any number of frames)
  *   status: device int (may be NULL), non-zero when a homography was singular */
 size_t mpiflow_render_workspace_bytes(int B, int S);
 size_t mpiflow_render_workspace_bytes_hw(int B, int S, int H, int W);

@@ -85,9 +85,35 @@ __global__ void plane_consts_kernel(const float *__restrict__ G, const float *__
 // H_tgt_src = K_t (R + t n^T / d) K_s^-1 with n = (0,0,1): the plane enters through column 2 of the middle factor
 // only, so when row 2 of K_s^-1 is (0, 0, 1) columns 0 and 1 of the product do not depend on the plane -- in fp32 as
 // well.  Checked on the computed matrices, bit for bit, so that the lean plane loop may hoist h0 x + h1 y.
-__global__ void batch_flags_kernel(const PlaneConst *__restrict__ pc, BatchConst *__restrict__ bcs, int S, int have_table)
+// Block B (only launched with a table): the key of the plane-spacing table kept in the workspace -- magic, S, H, W,
+// K_src^-1 of entry 0 and the plane depths, bit for bit.  key[TABLE_KEY_VALID] = 1 tells spacing_table_kernel that the
+// table in the workspace is the one this launch would compute (MPIFLOW_KEEP_TABLE); otherwise the key is rewritten.
+constexpr uint32_t TABLE_KEY_MAGIC = 0x4D504954u;
+constexpr int TABLE_KEY_VALID = 13, TABLE_KEY_DEPTHS = 16;
+__global__ void batch_flags_kernel(const PlaneConst *__restrict__ pc, BatchConst *__restrict__ bcs, int B, int S, int H, int W,
+                                   int have_table, int keep, uint32_t *__restrict__ key)
 {
     const int b = blockIdx.x, lane = threadIdx.x;
+    if (b == B) {
+        auto want = [&](int i) -> uint32_t {
+            if (i == 0) return TABLE_KEY_MAGIC;
+            if (i == 1) return (uint32_t)S;
+            if (i == 2) return (uint32_t)H;
+            if (i == 3) return (uint32_t)W;
+            if (i < 13) return __float_as_uint(bcs[0].kinv[i - 4]);
+            if (i < TABLE_KEY_DEPTHS) return 0u;
+            return __float_as_uint(pc[i - TABLE_KEY_DEPTHS].depth);
+        };
+        bool match = keep != 0;
+        for (int i = lane; i < TABLE_KEY_DEPTHS + S && match; i += 32)
+            if (i != TABLE_KEY_VALID) match = key[i] == want(i);
+        match = __all_sync(0xffffffffu, match);
+        if (!match)
+            for (int i = lane; i < TABLE_KEY_DEPTHS + S; i += 32)
+                if (i != TABLE_KEY_VALID) key[i] = want(i);
+        if (lane == 0) key[TABLE_KEY_VALID] = match ? 1u : 0u;
+        return;
+    }
     const PlaneConst *p0 = pc + (size_t)b * S;
     bool same = true, shared = have_table != 0;
     for (int s = lane; s < S; s += 32) {
@@ -105,7 +131,7 @@ __global__ void batch_flags_kernel(const PlaneConst *__restrict__ pc, BatchConst
     }
 }
 
-constexpr int TABLE_PLANES = 4;   // planes per thread of spacing_table_kernel
+constexpr int TABLE_PLANES = 8;   // planes per thread of spacing_table_kernel
 
 // Plane spacing of the source frame for batch entry 0, table[s][y][x] = | fl(ray * depth[s+1]) - fl(ray * depth[s]) |
 // (1e3 for the last plane, mpi_rendering.py:104-120), with exactly the operations of the plane loop of render_pk.cuh.
@@ -113,17 +139,24 @@ constexpr int TABLE_PLANES = 4;   // planes per thread of spacing_table_kernel
 // launch computes it once (0.13 GB at 1280x384x64, a few microseconds per frame) instead of per frame and plane.
 __global__ void __launch_bounds__(128)
 spacing_table_kernel(const PlaneConst *__restrict__ pc, const BatchConst *__restrict__ bcs, int S, int H,
-                     int W, float *__restrict__ table)
+                     int W, float *__restrict__ table, const uint32_t *__restrict__ key)
 {
-    // grid (W / 128, H, S / TABLE_PLANES): a few planes per thread keep enough loads and stores in flight for the
-    // 4 S H W bytes to stream at memory speed (one thread per pixel over all S planes ran at 2 TB/s)
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (key[TABLE_KEY_VALID]) return;      // the workspace already holds this very table (MPIFLOW_KEEP_TABLE)
+    // grid (W / 512, H, S / TABLE_PLANES), W % 4 == 0: four pixels (one 16-byte store) and eight planes per thread --
+    // enough stores in flight per thread and few enough blocks (a thread per pixel and four planes was bound by the
+    // block launch rate: 61 k blocks, 63 us for 126 MB)
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x >= W) return;
-    const float xf = (float)x, yf = (float)y;
+    const float yf = (float)y;
     const float *k = bcs[0].kinv;
-    const float r0 = mf_dot3(__ldg(k + 0), __ldg(k + 1), __ldg(k + 2), xf, yf);
-    const float r1 = mf_dot3(__ldg(k + 3), __ldg(k + 4), __ldg(k + 5), xf, yf);
-    const float r2 = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
+    float r0[4], r1[4], r2[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float xf = (float)(x + i);
+        r0[i] = mf_dot3(__ldg(k + 0), __ldg(k + 1), __ldg(k + 2), xf, yf);
+        r1[i] = mf_dot3(__ldg(k + 3), __ldg(k + 4), __ldg(k + 5), xf, yf);
+        r2[i] = mf_dot3(__ldg(k + 6), __ldg(k + 7), __ldg(k + 8), xf, yf);
+    }
     const size_t HW = (size_t)H * W, q = (size_t)y * W + x;
     const int s0 = blockIdx.z * TABLE_PLANES;
 #pragma unroll
@@ -131,12 +164,17 @@ spacing_table_kernel(const PlaneConst *__restrict__ pc, const BatchConst *__rest
         const int s = s0 + u;
         if (s >= S) break;
         const float dn = __ldg(&pc[s].depth_next), da = __ldg(&pc[s].depth);
-        const float ex = __fsub_rn(__fmul_rn(r0, dn), __fmul_rn(r0, da));
-        const float ey = __fsub_rn(__fmul_rn(r1, dn), __fmul_rn(r1, da));
-        const float ez = __fsub_rn(__fmul_rn(r2, dn), __fmul_rn(r2, da));
-        // torch.norm over the 3-vector on CUDA: ((x^2 + y^2) + z^2) with every square rounded, then sqrt.rn
-        const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-        table[(size_t)s * HW + q] = (s + 1 == S) ? 1e3f : sqrtf(fmaxf(e2, 1e-30f));
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float ex = __fsub_rn(__fmul_rn(r0[i], dn), __fmul_rn(r0[i], da));
+            const float ey = __fsub_rn(__fmul_rn(r1[i], dn), __fmul_rn(r1[i], da));
+            const float ez = __fsub_rn(__fmul_rn(r2[i], dn), __fmul_rn(r2[i], da));
+            // torch.norm over the 3-vector on CUDA: ((x^2 + y^2) + z^2) with every square rounded, then sqrt.rn
+            const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+            v[i] = (s + 1 == S) ? 1e3f : sqrtf(fmaxf(e2, 1e-30f));
+        }
+        *reinterpret_cast<float4 *>(table + (size_t)s * HW + q) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -303,7 +341,8 @@ MPIFLOW_API size_t mpiflow_render_workspace_bytes(int B, int S)
 MPIFLOW_API size_t mpiflow_render_workspace_bytes_hw(int B, int S, int H, int W)
 {
     if (B <= 0 || S <= 0 || H <= 0 || W <= 0) return 0;
-    return mpiflow_render_workspace_bytes(B, S) + align_up((size_t)S * H * W * sizeof(float), 256);
+    return mpiflow_render_workspace_bytes(B, S) + align_up((size_t)S * H * W * sizeof(float), 256) +
+           align_up((size_t)(TABLE_KEY_DEPTHS + S) * sizeof(uint32_t), 256);
 }
 
 // ---- TMA path ------------------------------------------------------------------------------------
@@ -469,11 +508,12 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     MF_CHECK_ARG(rgb && sigma && disparity && G && Kinv && Kt && workspace);
     MF_CHECK_ARG(out_rgb && out_depth && out_mask && out_flow);
     MF_CHECK_ARG(B > 0 && S > 0 && H > 0 && W > 0 && B <= 65535 && (int64_t)H * W < (1ll << 31));
-    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW | 0xffff00u)) == 0);
+    MF_CHECK_ARG((flags & ~(MPIFLOW_BG_DEPTH_INF | MPIFLOW_HARD_FLOW | MPIFLOW_KEEP_TABLE | 0xffff00u)) == 0);
     const int poses = (int)((flags >> 8) & 0xffu) + 1;
     const int reserve_sms = (int)((flags >> 16) & 0xffu);
     MF_CHECK_ARG(B % poses == 0);
-    flags &= ~0xffff00u;
+    const bool keep_table = (flags & MPIFLOW_KEEP_TABLE) != 0;
+    flags &= ~(0xffff00u | MPIFLOW_KEEP_TABLE);
     MF_CHECK_ARG(((uintptr_t)workspace & 15) == 0);
     if (workspace_bytes < mpiflow_render_workspace_bytes(B, S)) return MPIFLOW_E_WORKSPACE;
     const size_t smem = (size_t)S * sizeof(PlaneConst);
@@ -494,14 +534,16 @@ int mf_render_fused_impl(const float *rgb, int64_t rgb_sb, int64_t rgb_ss, int64
     // can describe it.  Entries whose K_src^-1 or plane depths differ from entry 0 evaluate it in the plane loop.
     static const bool table_off = []() { const char *e = getenv("MPIFLOW_PK_SPACING_TABLE"); return e && atoi(e) == 0; }();
     const size_t base_bytes = mpiflow_render_workspace_bytes(B, S);
-    const bool have_table = !f16 && !table_off && render_path() == 0 && B >= 4 && (W % 4) == 0 &&
+    const bool have_table = !f16 && !table_off && render_path() == 0 && (B >= 4 || keep_table) && (W % 4) == 0 &&
                             workspace_bytes >= mpiflow_render_workspace_bytes_hw(B, S, H, W);
     float *table = have_table ? reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + base_bytes) : nullptr;
-    batch_flags_kernel<<<B, 32, 0, st>>>(pc, bc, S, have_table ? 1 : 0);
+    uint32_t *table_key = have_table ? reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(table) +
+                                                                    align_up((size_t)S * H * W * sizeof(float), 256)) : nullptr;
+    batch_flags_kernel<<<B + (have_table ? 1 : 0), 32, 0, st>>>(pc, bc, B, S, H, W, have_table ? 1 : 0, keep_table ? 1 : 0, table_key);
     rc = mf_launch_status();
     if (rc) return rc;
     if (have_table) {
-        spacing_table_kernel<<<dim3((W + 127) / 128, H, (S + TABLE_PLANES - 1) / TABLE_PLANES), 128, 0, st>>>(pc, bc, S, H, W, table);
+        spacing_table_kernel<<<dim3((W / 4 + 127) / 128, H, (S + TABLE_PLANES - 1) / TABLE_PLANES), 128, 0, st>>>(pc, bc, S, H, W, table, table_key);
         rc = mf_launch_status();
         if (rc) return rc;
     }

@@ -20,6 +20,16 @@ from utils.mpi.rendering_utils import transform_G_xyz, sample_pdf, gather_pixel_
 # reference pays a full GPU->CPU->GPU round trip); set False for fully asynchronous operation
 CHECK_SINGULAR = True
 
+# render_fused keeps one workspace per (device, stream, shape) between calls so that the plane-spacing table is
+# computed once per (K_src^-1, disparities) (MPIFLOW_KEEP_TABLE); False: a fresh workspace per call, as in round 1
+KEEP_WORKSPACES = True
+_workspaces = {}
+
+
+def release_workspaces():
+    """drop the cached workspaces (one S*H*W-float table each)"""
+    _workspaces.clear()
+
 
 def _flags(is_bg_depth_inf=False, hard_flow=False):
     return (nat.BG_DEPTH_INF if is_bg_depth_inf else 0) | (nat.HARD_FLOW if hard_flow else 0)
@@ -270,14 +280,28 @@ def render_fused(mpi_rgb_src, mpi_sigma_src, mpi_disparity_src, G_tgt_src, K_src
         out = (new(3), new(1), new(1), new(2), new(1) if obj is not None else None)
     o_rgb, o_depth, o_mask, o_flow, o_obj = out
     L = nat.lib()
-    ws_bytes = L.mpiflow_render_workspace_bytes_hw(B, S, H, W) if B >= 4 else L.mpiflow_render_workspace_bytes(B, S)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    # One workspace per (device, stream, shape), kept between calls: the plane-spacing table in it is then computed once
+    # per (K_src^-1, disparities) instead of once per call (MPIFLOW_KEEP_TABLE; the library checks the key on the
+    # device), which is what a generator loop with fixed intrinsics wants -- single frames and pose pairs included.
+    keep = 4 if (KEEP_WORKSPACES and W % 4 == 0 and not half) else 0
+    if keep:
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream, B, S, H, W)
+        ws = _workspaces.get(key)
+        if ws is None:
+            if len(_workspaces) >= 8:
+                _workspaces.clear()
+            # zeroed once: recycled allocator memory may hold the key of an earlier table whose data has been overwritten
+            ws = _workspaces[key] = torch.zeros(L.mpiflow_render_workspace_bytes_hw(B, S, H, W), dtype=torch.uint8, device=device)
+        ws_bytes = ws.numel()
+    else:
+        ws_bytes = L.mpiflow_render_workspace_bytes_hw(B, S, H, W) if B >= 4 else L.mpiflow_render_workspace_bytes(B, S)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
     entry = L.mpiflow_render_fused_f16 if half else L.mpiflow_render_fused_f32
     nat.check(entry(
         nat.ptr(rgb), rgb.stride(0), rgb.stride(1), rgb.stride(2), nat.ptr(sig), sig.stride(0), sig.stride(1),
         nat.ptr(obj), obj_sb, obj_ss, nat.ptr(disp), nat.ptr(G), nat.ptr(kinv), nat.ptr(kt), B, S, H, W,
-        _flags(is_bg_depth_inf, hard_flow) | ((poses_per_mpi - 1) << 8), nat.ptr(o_rgb), nat.ptr(o_depth), nat.ptr(o_mask), nat.ptr(o_flow),
+        _flags(is_bg_depth_inf, hard_flow) | ((poses_per_mpi - 1) << 8) | keep, nat.ptr(o_rgb), nat.ptr(o_depth), nat.ptr(o_mask), nat.ptr(o_flow),
         nat.ptr(o_obj), nat.ptr(ws), ws_bytes, nat.ptr(status), nat.stream(rgb)))
     if CHECK_SINGULAR and int(status.item()):
         raise Exception("Matrix inverse contains nan!")

@@ -19,6 +19,7 @@ namespace portion, so with this directory first on sys.path `utils.utils` and `u
 `utils.transform`, `utils.flow_viz`, ... still resolve to the reference's files further down the path.
 """
 import math
+import os
 import random
 
 import numpy as np
@@ -249,5 +250,13 @@ def render_3dphoto_dynamic(opt, src_imgs, obj_mask, disp, mpi_all_src, disparity
     flow_mix, frame_mix, fill_mask, _ = render_sample_pair(
         src_imgs, obj_mask, mpi_all_src, disparity_all_src, k_src, k_tgt, cam_ext, cam_ext_dynamic, hard_flow,
         mask_thresh)
-    inpainted = inpaint_ns(frame_mix, fill_mask, 3)                                         # :284-286, on the device
-    return flow_mix.cpu().numpy(), src_np, inpainted.cpu().numpy(), None
+    # :284-286.  One sample at a time the reference's own host call is the faster of two bit-identical routes (a single
+    # image is one serial march: 7-12 ms in OpenCV on a host core, 5-25 ms on one warp of the GPU); batches belong on
+    # the device (inpaint_ns on N images, sample_writer.SampleWriter(device_inpaint=True)).  MPIFLOW_INPAINT=device
+    # keeps this call on the GPU as well.
+    if os.environ.get("MPIFLOW_INPAINT", "host") == "device":
+        inpainted = inpaint_ns(frame_mix, fill_mask, 3).cpu().numpy()
+    else:
+        import cv2
+        inpainted = cv2.inpaint(frame_mix.cpu().numpy(), fill_mask.cpu().numpy(), 3, cv2.INPAINT_NS)
+    return flow_mix.cpu().numpy(), src_np, inpainted, None

@@ -199,6 +199,21 @@ def test_render_3dphoto_dynamic_end_to_end(gold):
 
 
 @pytest.mark.gpu
+def test_render_3dphoto_dynamic_device_and_host_hole_filling_agree(gold, monkeypatch):
+    """MPIFLOW_INPAINT=device keeps the hole filling on the GPU (csrc/inpaint.cu): the same bytes as the host call"""
+    pytest.importorskip("cv2")
+    from utils import utils as U
+    mpi, src, obj, disp, K = _dev(gold, "in_mpi", "in_src", "in_obj", "in_disparity", "in_K")
+    opt = types.SimpleNamespace(ext_cz=float(gold["ext_cz"]))
+    outs = []
+    for backend in ("host", "device"):
+        monkeypatch.setenv("MPIFLOW_INPAINT", backend)
+        random.seed(int(gold["meta"][4]))
+        outs.append(U.render_3dphoto_dynamic(opt, src, obj, None, mpi, disp, K, K, name="sample.png"))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][2], outs[1][2])
+
+
+@pytest.mark.gpu
 def test_poses_per_mpi_equals_materialised_batch():
     """MPIFLOW_POSES_PER_MPI(P): frames b*P..b*P+P-1 read MPI b == the same launch on repeat_interleave'd MPIs"""
     import _native as nat
