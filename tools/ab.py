@@ -17,7 +17,9 @@ sys.path[:0] = [%r, %r]
 import bench
 dev = torch.device('cuda', 0)
 B = int(sys.argv[1]); steps = int(sys.argv[2])
-calls = [bench.FusedCall(bench.make_device_batch(B, 114514 + i, dev), dev) for i in range(2)]
+import os
+flags = int(os.environ.get('AB_FLAGS', '0'), 0)   # e.g. 4 = MPIFLOW_KEEP_TABLE
+calls = [bench.FusedCall(bench.make_device_batch(B, 114514 + i, dev), dev, flags=flags) for i in range(2)]
 for i in range(5): calls[i %% 2]()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
