@@ -433,11 +433,18 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
 }  // namespace
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-// column segments the init kernel can keep row occupancies for in shared memory
-static int inpaint_maxc(int rows)
+// shared memory of inpaint_init_kernel without the row occupancies, and the column segments whose row occupancies fit
+// beside it (0: the image is too tall for the kernel)
+static size_t inpaint_init_fixed_smem(int rows, int cols)
 {
-    const int m = (150 * 1024) / (rows + 2);
-    return m < 1 ? 1 : m > MAXC ? MAXC : m;
+    return (size_t)(rows + 3 + 2 * MAXC + 4) * sizeof(int) + MAXSEG * sizeof(Rect) + 2 * (size_t)(cols + 2);
+}
+static int inpaint_maxc(int rows, int cols)
+{
+    const size_t budget = 200 * 1024, fixed = inpaint_init_fixed_smem(rows, cols);
+    if (fixed + (size_t)(rows + 2) > budget) return 0;
+    const size_t m = (budget - fixed) / (size_t)(rows + 2);
+    return m > (size_t)MAXC ? MAXC : (int)m;
 }
 
 MPIFLOW_API size_t mpiflow_inpaint_ns_workspace_bytes(int n, int rows, int cols)
@@ -474,9 +481,9 @@ MPIFLOW_API int mpiflow_inpaint_ns_u8(const uint8_t *img, const uint8_t *mask, i
         cudaError_t e = cudaMemcpyAsync(out, img, (size_t)n * rows * cols * 3, cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return (int)e;
     }
-    const int maxc = inpaint_maxc(rows);
-    const size_t smem = (size_t)(rows + 3 + 2 * MAXC + 4) * sizeof(int) + MAXSEG * sizeof(Rect) + 2 * (size_t)(cols + 2) +
-                        (size_t)maxc * (rows + 2);
+    const int maxc = inpaint_maxc(rows, cols);
+    MF_CHECK_ARG(maxc >= 1);                   // rows + cols beyond what the init kernel holds in shared memory
+    const size_t smem = inpaint_init_fixed_smem(rows, cols) + (size_t)maxc * (rows + 2);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(inpaint_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
