@@ -206,7 +206,7 @@ def render_sample_pairs(src_imgs, obj_masks, mpi_all_src, disparity_all_src, k_s
     return flow_mix, frame_mix, fill_mask
 
 
-_inpaint_ws = {}     # (device index, n, H, W) -> workspace tensor; reused across samples, never shrunk
+_inpaint_ws = {}     # (device index, stream, n, H, W) -> workspace tensor; reused across samples
 
 
 def inpaint_ns(frame, fill_mask, radius=3, out=None):
@@ -225,9 +225,11 @@ def inpaint_ns(frame, fill_mask, radius=3, out=None):
     if C != 3 or tuple(msk.shape) != (N, H, W):
         raise ValueError(f"inpaint_ns: image {tuple(frame.shape)} / mask {tuple(fill_mask.shape)}")
     L = nat.lib()
-    key = (img.device.index, N, H, W)
+    key = (img.device.index, torch.cuda.current_stream(img.device).cuda_stream, N, H, W)   # one per stream: calls on two streams must not share scratch
     ws = _inpaint_ws.get(key)
     if ws is None:
+        if len(_inpaint_ws) >= 8:
+            _inpaint_ws.clear()
         ws = torch.empty(L.mpiflow_inpaint_ns_workspace_bytes(N, H, W), dtype=torch.uint8, device=img.device)
         _inpaint_ws[key] = ws
     res = img if (out is frame and img.data_ptr() == frame.data_ptr()) else torch.empty_like(img)
