@@ -399,13 +399,21 @@ def run_ours(args, rank, local_rank, world):
                   "why_not_p2p": g.why_not_p2p,
                   "collective": ("copy-engine pulls of the packed 8 output channels out of the peers' symmetric memory "
                                  "(one stream per peer, device-side barriers), under the next render" if g.mode == "p2p" else
+                                 "copy-engine pushes of the packed 8 output channels into the peers' symmetric receive buffers "
+                                 "(one stream per peer, device-side barriers), under the next render" if g.mode == "push" else
                                  "one NCCL all_gather_into_tensor of the packed 8 output channels per step, preallocated, "
                                  "on a side stream overlapping the next render")}
         # the gathered frames are the rendered frames (slot 0 of the last even step, every rank's block)
-        if g.mode == "p2p":
-            torch.cuda.synchronize()
-            mine = g.views(0)[0][rank]
-            assert torch.equal(mine, gcalls[0].out[0]), "gathered block differs from the rendered one"
+        torch.cuda.synchronize()
+        mine = g.views(0)[0][rank]
+        assert torch.equal(mine, gcalls[0].out[0]), "gathered block differs from the rendered one"
+        # every rank holds every other rank's frames: compare checksums of what arrived with what each rank rendered
+        sums = torch.stack([v.double().sum() for v in g.views(0)[0]])
+        own = torch.zeros(world, dtype=torch.float64, device=device)
+        own[rank] = gcalls[0].out[0].double().sum()
+        dist.all_reduce(own)
+        assert torch.equal(sums, own), f"rank {rank}: gathered frames differ from the rendered ones"
+        gather["verified"] = "checksums of all ranks' blocks"
 
     # ---- end to end through the host-buffer C-ABI entry point ----
     Be = args.e2e_frames_per_step
@@ -612,7 +620,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=0, help="frames per launch per GPU (0 = the configuration's own)")
-    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"], help="transport of the output-gather leg")
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "push", "nccl"], help="transport of the output-gather leg")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to the output gather (with_output_gather leg)")
     ap.add_argument("--e2e-frames-per-step", type=int, default=2)
     ap.add_argument("--e2e-max-steps", type=int, default=20)

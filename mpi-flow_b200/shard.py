@@ -14,6 +14,8 @@ per step; `views(slot)` hands out the gathered frames as per-rank views.  Two tr
     (torch.distributed._symmetric_memory); after a device-side barrier every rank PULLS the other ranks' blocks straight
     out of their memory with copy-engine transfers, one side stream per peer.  No SM is used, so the gather runs under
     the persistent renderer, which occupies every SM for the whole launch.
+  * "push" (same requirements): the RECEIVE buffers live in symmetric memory instead and every rank writes its block
+    into the peers' receive buffers (posted NVLink writes instead of read round trips), between the same two barriers.
   * "nccl" (and gloo in the CPU tests): a single `all_gather_into_tensor` on a side stream.  NCCL's kernel needs SMs;
     pass MPIFLOW_RESERVE_SMS(n) to the renderer to leave it some.
 """
@@ -56,17 +58,41 @@ class FrameGatherer:
         self.done = [None] * slots
         self.mode, self.why_not_p2p = "nccl" if self.cuda else dist.get_backend(group), None
         self.send = None
-        if self.cuda and mode in ("auto", "p2p") and self.world > 1:
+        self.recv = None
+        if self.cuda and mode in ("auto", "p2p", "push") and self.world > 1:
             try:
-                self._setup_p2p(slots, dtype)
-                self.mode = "p2p"
+                if mode == "push":
+                    self._setup_push(slots, dtype)
+                else:
+                    self._setup_p2p(slots, dtype)
+                self.mode = "push" if mode == "push" else "p2p"
             except Exception as e:  # noqa: BLE001 -- no symmetric memory / no peer access: the collective still works
-                if mode == "p2p":
+                if mode in ("p2p", "push"):
                     raise
                 self.why_not_p2p = f"{type(e).__name__}: {e}"[:200]
         if self.send is None:
             self.send = [torch.zeros(self.block, dtype=dtype, device=self.device) for _ in range(slots)]
-        self.recv = [torch.empty(self.world * self.block, dtype=dtype, device=self.device) for _ in range(slots)]
+        if self.recv is None:
+            self.recv = [torch.empty(self.world * self.block, dtype=dtype, device=self.device) for _ in range(slots)]
+
+    def _setup_push(self, slots, dtype):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        recv, handles = [], []
+        for _ in range(slots):
+            t = symm_mem.empty(self.world * self.block, dtype=dtype, device=self.device)
+            t.zero_()
+            handles.append(symm_mem.rendezvous(t, grp))
+            recv.append(t)
+        # every peer's receive buffer of every slot, as tensors in this process's address space (NVLink stores)
+        self.peer_recv = [[h.get_buffer(r, (self.world * self.block,), dtype) for r in range(self.world)] for h in handles]
+        self.handles = handles
+        self.pull_streams = [torch.cuda.Stream(self.device) for _ in range(self.world - 1)]
+        torch.cuda.synchronize(self.device)
+        handles[0].barrier()
+        torch.cuda.synchronize(self.device)
+        self.recv = recv
+        self.send = [torch.zeros(self.block, dtype=dtype, device=self.device) for _ in range(slots)]
 
     def _setup_p2p(self, slots, dtype):
         import torch.distributed._symmetric_memory as symm_mem
@@ -105,6 +131,29 @@ class FrameGatherer:
             return
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device))
+        if self.mode == "push":
+            h, mine = self.handles[slot], self.send[slot]
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                h.barrier()                      # every rank is done with the previous content of its receive buffer
+                fence = torch.cuda.Event()
+                fence.record(self.side)
+            pushed = []
+            for k, st in enumerate(self.pull_streams):      # one copy-engine stream per peer
+                r = (self.rank + 1 + k) % self.world
+                with torch.cuda.stream(st):
+                    st.wait_event(fence)
+                    self.peer_recv[slot][r][self.rank * self.block: (self.rank + 1) * self.block].copy_(mine, non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(st)
+                    pushed.append(e)
+            with torch.cuda.stream(self.side):
+                for e in pushed:
+                    self.side.wait_event(e)
+                h.barrier()                      # every rank's writes have landed: the receive buffers are complete
+                self.done[slot] = torch.cuda.Event()
+                self.done[slot].record(self.side)
+            return
         if self.mode == "p2p":
             h, recv = self.handles[slot], self.recv[slot]
             with torch.cuda.stream(self.side):
@@ -142,7 +191,7 @@ class FrameGatherer:
 
     def views(self, slot):
         """per channel, the list over ranks of that rank's frames [n_r, c, H, W] (views of the receive buffer)"""
-        own = self.send[slot] if self.mode == "p2p" else None         # p2p pulls the peers' blocks only
+        own = self.send[slot] if self.mode in ("p2p", "push") else None     # peer memory moves the peers' blocks only
         per_rank = [self._split(own if (own is not None and r == self.rank) else self.recv[slot][r * self.block: (r + 1) * self.block],
                                 hi - lo) for r, (lo, hi) in enumerate(self.spans)]
         return [[per_rank[r][c] for r in range(self.world)] for c in range(len(self.channels))]
