@@ -268,6 +268,11 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
         }
     }
     __syncwarp();
+    // this lane's window position of the first 32 (r = (i - k, j - l), |r|^2, 1 / (|r|^4 + 1))
+    const int od0 = sm.off[lane < nwin ? lane : 0], dk0 = od0 >> 16, dl0 = (int)(short)(od0 & 0xffff);
+    const float ry0 = (float)(-dk0), rx0 = (float)(-dl0);
+    const float rl0 = __fadd_rn(__fmul_rn(rx0, rx0), __fmul_rn(ry0, ry0));
+    const float dst0 = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(rl0, rl0), 1.f));
     uint32_t seq = (uint32_t)nc;
     int np = 0;
 
@@ -303,7 +308,15 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
                 int nvalid = 0;
                 for (int base = 0; base < nwin; base += 32) {
                     const int p = base + lane;
-                    const int od = sm.off[p < nwin ? p : 0], dk = od >> 16, dl = (int)(short)(od & 0xffff);
+                    int dk = dk0, dl = dl0;                       // radius <= 3: one position per lane, fixed for the launch
+                    float ry = ry0, rx = rx0, rl = rl0, dst = dst0;
+                    if (base) {
+                        const int od = sm.off[p < nwin ? p : 0];
+                        dk = od >> 16; dl = (int)(short)(od & 0xffff);
+                        ry = (float)(-dk); rx = (float)(-dl);
+                        rl = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+                        dst = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(rl, rl), 1.f));
+                    }
                     const int k = i + dk, l = j + dl, kl = k * ecols + l;
                     bool valid = p < nwin && (interior || (k > 0 && l > 0 && k < erows - 1 && l < ecols - 1));
                     if (valid) valid = f[kl] != INSIDE;
@@ -311,9 +324,6 @@ inpaint_ns_march_kernel(int rows, int cols, int range, uint8_t *f_all, float *t_
                     if (valid) {
                         const bool fdn = f[kl + ecols] != INSIDE, fup = f[kl - ecols] != INSIDE;
                         const bool frt = f[kl + 1] != INSIDE, flf = f[kl - 1] != INSIDE;
-                        const float ry = (float)(-dk), rx = (float)(-dl);
-                        const float rl = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-                        const float dst = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(rl, rl), 1.f));
                         if (interior) {
                             const uint8_t *c0 = out + ((k - 1) * cols + (l - 1)) * 3;
                             const int rs = cols * 3;
