@@ -498,6 +498,7 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": launches * args.steps,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "frac_of_datasheet_8TBps": round(achieved / 8000.0, 4),
                          "kernel": "render_fused_pk_kernel (persistent, warp-specialised; step = prologue + this kernel)",
                          "bytes_per_launch": int(bytes_per_launch),
                          "bound_note": "algorithmic HBM bytes vs measured copy bandwidth (DESIGN.md 5.1)"},
