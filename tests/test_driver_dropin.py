@@ -142,6 +142,17 @@ def test_unmodified_generator_runs_in_half_precision(tmp_path):
             assert np.abs(dst.astype(np.int32) - src.astype(np.int32)).mean() < 40
         if name == "a":
             assert np.abs(src.astype(np.int32) - src_in.astype(np.int32)).max() <= 1    # fp16 round trip of the image
+    # the same run with the hole filling on the GPU (MPIFLOW_INPAINT=device): the same files, byte for byte after decoding
+    out2 = tmp_path / "out_device"
+    r = subprocess.run([sys.executable, DRIVER, "--width", "160", "--height", "96", "--repeat", "2", "--base",
+                        str(tmp_path / "base"), "--out", str(out2), "--ckpt_path", str(tmp_path / "ck.pth")],
+                       cwd=str(tmp_path), env=dict(env, MPIFLOW_INPAINT="device"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for name in ("a", "b"):
+        for rep in range(2):
+            for sub in ("dst_images", "src_images"):
+                assert np.array_equal(cv2.imread(str(out / sub / f"{name}_{rep}.png")), cv2.imread(str(out2 / sub / f"{name}_{rep}.png")))
+            assert np.array_equal(readFlow(str(out / "flows" / f"{name}_{rep}.flo")), readFlow(str(out2 / "flows" / f"{name}_{rep}.flo")))
 
 
 def test_reference_modules_run_on_cpu_tensors_even_where_cuda_exists(monkeypatch):
