@@ -232,7 +232,9 @@ def inpaint_ns(frame, fill_mask, radius=3, out=None):
             _inpaint_ws.clear()
         ws = torch.empty(L.mpiflow_inpaint_ns_workspace_bytes(N, H, W), dtype=torch.uint8, device=img.device)
         _inpaint_ws[key] = ws
-    res = img if (out is frame and img.data_ptr() == frame.data_ptr()) else torch.empty_like(img)
+    if out is not None and (out is not frame or img.data_ptr() != frame.data_ptr()):
+        raise ValueError("inpaint_ns: out must be None or the (contiguous) frame itself (in place)")
+    res = img if out is frame else torch.empty_like(img)
     nat.check(L.mpiflow_inpaint_ns_u8(nat.ptr(img), nat.ptr(msk), N, H, W, int(round(radius)), nat.ptr(res), nat.ptr(ws),
                                       ws.numel(), nat.stream(img)))
     return res[0] if single else res

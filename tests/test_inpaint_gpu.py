@@ -90,5 +90,7 @@ def test_argument_errors():
         U.inpaint_ns(img.cpu(), torch.zeros((8, 8), dtype=torch.uint8))
     with pytest.raises(TypeError):
         U.inpaint_ns(img.float(), torch.zeros((8, 8), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        U.inpaint_ns(img, torch.zeros((8, 8), dtype=torch.uint8, device="cuda"), out=torch.empty_like(img))     # in place or nothing
     with pytest.raises(nat.MpiflowError):
         U.inpaint_ns(img, torch.zeros((8, 8), dtype=torch.uint8, device="cuda"), radius=9)   # window larger than the kernel's
