@@ -149,6 +149,32 @@ def test_sample_pairs_at_full_size_against_two_independent_reference_renders():
             check(errors(got, want, 2 * n + j), f"sample {n} pose {j}")
 
 
+@needs_ref
+def test_sample_pair_with_an_instance_mask_like_the_generator():
+    """the generator's mask is ONE instance's binary mask, bilinearly resized with align_corners=True
+    (gen_3dphoto_dynamic_v2.py:101-105): constant over most of the frame, soft only along the object's outline; the
+    pair renders it as obj and 1 - obj on a shared MPI (utils/utils.py:210-238)"""
+    from utils import utils as U
+    S, H, W = 64, 384, 1280
+    d = device_batch(1, S, H, W, synth.SEED + 21)
+    yy, xx = torch.meshgrid(torch.arange(H // 2, dtype=torch.float32), torch.arange(W // 2, dtype=torch.float32), indexing="ij")
+    inst = ((((xx - 0.4 * W / 2) / (0.18 * W / 2)) ** 2 + ((yy - 0.55 * H / 2) / (0.3 * H / 2)) ** 2) < 1).float()
+    obj = torch.nn.functional.interpolate(inst[None, None].cuda(), size=(H, W), mode="bilinear", align_corners=True)
+    assert 0.05 < float(obj.mean()) < 0.5 and float(((obj > 0) & (obj < 1)).float().mean()) < 0.02
+    cam_obj = torch.from_numpy(synth.poses(1, "object", 7)).cuda()[0]
+    flow_mix, frame_mix, fill_mask, (rgb2, obj2, flow2) = U.render_sample_pair(
+        d["mpi"][:, 0, 0:3].contiguous(), obj, d["mpi"], d["disparity"], d["K"], d["K"], cam_obj, d["G"][0], k_src_inv=d["Kinv"])
+    torch.cuda.synchronize()
+    blended = U.blend_src_into_mpi(d["mpi"][:, 0, 0:3].contiguous(), d["mpi"][:, :, 0:3], d["mpi"][:, :, 3:], d["disparity"], d["Kinv"])
+    mpi_b = torch.cat((blended, d["mpi"][:, :, 3:]), 2)
+    for j, (pose, m) in enumerate(((cam_obj, obj), (d["G"][0], 1 - obj))):
+        with torch.no_grad():
+            want = ref_modules.render_frame(mpi_b, d["disparity"], pose[None], d["Kinv"], d["K"], m)
+        assert float((rgb2[j:j + 1] - want[0]).abs().max()) <= TOL, j
+        assert float((obj2[j:j + 1] - want[4]).abs().max()) <= TOL, j
+        assert float((flow2[j:j + 1] - want[3]).abs().max()) <= TOL, j             # raw renders: the clip of :347 comes with the merge
+
+
 def test_poses_per_mpi_with_footprints_beyond_the_box():
     """MPIFLOW_POSES_PER_MPI(2) with N >= 2 distinct MPIs and a strong zoom-out pose: some footprints do not fit the
     TMA box, those planes are read from global memory and must come from the frame's own MPI (index b / poses)."""
