@@ -227,19 +227,19 @@ def sample_assembly_leg(d, steps=24):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
-def hole_filling_leg(device, batch=32, steps=3):
+def hole_filling_leg(device, batch=148, unique=8, steps=3):
     """SURVEY 8(f) row 4 next to the headline: cv2.inpaint(INPAINT_NS) of the generator (utils/utils.py:284-286) on the
     device, a batch of generator-like masks (the disocclusion ring of one moved object + the strips a camera move
-    uncovers at the border, 1.7 % holes).  One image is checked against the C restatement of OpenCV's algorithm
+    uncovers at the border, 1.7 % holes; `unique` different images repeated to one image per SM).  One image is checked against the C restatement of OpenCV's algorithm
     (oracle/inpaint_oracle.c, pinned against cv2), which is also timed on one host core.  Reported beside the metric."""
     try:
         from utils import utils as U
         g = torch.Generator().manual_seed(synth.SEED)
-        img = torch.nn.functional.avg_pool2d(torch.rand((batch, 3, H + 8, W + 8), generator=g), 9, 1)     # smooth, HxW
+        img = torch.nn.functional.avg_pool2d(torch.rand((unique, 3, H + 8, W + 8), generator=g), 9, 1)     # smooth, HxW
         img = (img * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
         yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
         masks = []
-        for n in range(batch):
+        for n in range(unique):
             dx, dy = 3 + n % 4, (n % 7) - 3
             a = ((xx - 0.4 * W) / (0.18 * W)) ** 2 + ((yy - 0.55 * H) / (0.3 * H)) ** 2 < 1
             b = ((xx - 0.4 * W - dx) / (0.18 * W)) ** 2 + ((yy - 0.55 * H - dy) / (0.3 * H)) ** 2 < 1
@@ -248,7 +248,8 @@ def hole_filling_leg(device, batch=32, steps=3):
             m[:3, :] = True
             masks.append(m)
         mask = torch.stack(masks).to(torch.uint8)
-        d_img, d_mask = img.to(device), mask.to(device)
+        rep = [n % unique for n in range(batch)]
+        d_img, d_mask = img.to(device)[rep].contiguous(), mask.to(device)[rep].contiguous()
         out = U.inpaint_ns(d_img, d_mask, 3)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
