@@ -303,20 +303,45 @@ splat_chain_resolve_kernel(const int *__restrict__ head, const int *__restrict__
         if (k2 < 0) {                                          // one writer: the common case
             if (z[k] < 1000.f) win = k;
         } else {
-            int ks[CHAIN_MAX];
-            int cnt = 0;
-            for (int c = k; c >= 0; c = next[c]) {
-                if (cnt == CHAIN_MAX) { *overflow = 1; touched = false; break; }   // left to the radix path
-                int j = cnt++;                                 // insertion sort by raster index
-                while (j > 0 && ks[j - 1] > c) { ks[j] = ks[j - 1]; j--; }
-                ks[j] = c;
-            }
-            if (touched)
-                for (int i = 0; i < cnt; i++) {
-                    const float zi = z[ks[i]];
-                    if (zi < zprev) win = ks[i];               // :19-21 (for the last writer zprev is its dlut)
-                    if (i + 1 < cnt) zprev = zi;               // :28 unconditionally
+            // two to four writers (nearly all colliding targets): ordered in registers by a sorting network; the loads of
+            // z are independent of each other
+            const int k3 = next[k2], k4 = k3 >= 0 ? next[k3] : -1, k5 = k4 >= 0 ? next[k4] : -1;
+            if (k5 < 0) {
+                const int BIG = 0x7fffffff;
+                int a = k, b = k2, c = k3 >= 0 ? k3 : BIG, d = k4 >= 0 ? k4 : BIG;
+                auto cswap = [](int &x, int &y) { const int lo = min(x, y), hi = max(x, y); x = lo; y = hi; };
+                cswap(a, b); cswap(c, d); cswap(a, c); cswap(b, d); cswap(b, c);
+                const float za = z[a], zb = z[b], zc = c != BIG ? z[c] : 0.f, zd = d != BIG ? z[d] : 0.f;
+                const int cnt = 2 + (c != BIG) + (d != BIG);
+                if (za < zprev) win = a;                       // :19-21, then :28 unconditionally
+                zprev = za;
+                if (cnt == 2) { if (zb < zprev) win = b; }
+                else {
+                    if (zb < zprev) win = b;
+                    zprev = zb;
+                    if (cnt == 3) { if (zc < zprev) win = c; }
+                    else {
+                        if (zc < zprev) win = c;
+                        zprev = zc;
+                        if (zd < zprev) win = d;
+                    }
                 }
+            } else {
+                int ks[CHAIN_MAX];
+                int cnt = 0;
+                for (int c = k; c >= 0; c = next[c]) {
+                    if (cnt == CHAIN_MAX) { *overflow = 1; touched = false; break; }   // left to the radix path
+                    int j = cnt++;                             // insertion sort by raster index
+                    while (j > 0 && ks[j - 1] > c) { ks[j] = ks[j - 1]; j--; }
+                    ks[j] = c;
+                }
+                if (touched)
+                    for (int i = 0; i < cnt; i++) {
+                        const float zi = z[ks[i]];
+                        if (zi < zprev) win = ks[i];           // :19-21 (for the last writer zprev is its dlut)
+                        if (i + 1 < cnt) zprev = zi;           // :28 unconditionally
+                    }
+            }
         }
     }
     uint8_t *o = staged ? reinterpret_cast<uint8_t *>(stage) + threadIdx.x * 5 : warped + (size_t)t * 5;
