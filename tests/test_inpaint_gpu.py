@@ -94,3 +94,36 @@ def test_argument_errors():
         U.inpaint_ns(img, torch.zeros((8, 8), dtype=torch.uint8, device="cuda"), out=torch.empty_like(img))     # in place or nothing
     with pytest.raises(nat.MpiflowError):
         U.inpaint_ns(img, torch.zeros((8, 8), dtype=torch.uint8, device="cuda"), radius=9)   # window larger than the kernel's
+
+
+def test_holes_at_the_independence_boundary():
+    """the device path marches holes that are >= radius + 2 columns (or rows) apart separately: holes placed exactly
+    radius + 1, + 2 and + 3 apart, in columns and in rows, on white noise (any leak between two marches shows), for
+    radii 1..4; plus 25 random layouts -- all against the pinned C restatement"""
+    from utils import utils as U
+    rng = np.random.default_rng(99)
+    H, W = 72, 120
+    cases = []
+    for radius in (1, 2, 3, 4):
+        for gap in (radius + 1, radius + 2, radius + 3):
+            img = (rng.random((H, W, 3)) * 255).astype(np.uint8)
+            mask = np.zeros((H, W), np.uint8)
+            x = 10
+            for _ in range(4):                      # vertical bars `gap` columns apart (first hole column to next)
+                mask[8:40, x:x + 3] = 1
+                x += 2 + gap                        # last column of a bar = x + 2, next bar starts `gap` columns later
+            y = 44
+            for _ in range(3):                      # horizontal bars `gap` rows apart, in their own column range
+                mask[y:y + 2, 60:110] = 1
+                y += 1 + gap
+            cases.append((img, mask, radius))
+    for _ in range(25):
+        img = (rng.random((H, W, 3)) * 255).astype(np.uint8)
+        mask = np.zeros((H, W), np.uint8)
+        for _ in range(int(rng.integers(3, 12))):
+            x0, y0 = int(rng.integers(0, W - 8)), int(rng.integers(0, H - 8))
+            mask[y0:y0 + int(rng.integers(1, 8)), x0:x0 + int(rng.integers(1, 8))] = 1
+        cases.append((img, mask, int(rng.integers(1, 5))))
+    for n, (img, mask, radius) in enumerate(cases):
+        got = U.inpaint_ns(_dev(img), _dev(mask), radius).cpu().numpy()
+        assert np.array_equal(got, io.inpaint_ns(img, mask, radius)), (n, radius)
